@@ -1,0 +1,485 @@
+// Elementwise probability / fusion surfaces (a7-a11, a13, a14), BlockMaxIndex
+// builders (a12), the multi-shard merge (K7) and the dense fp64 top-k (a15).
+#include "bb25_internal.cuh"
+
+namespace bb25 {
+
+enum {
+    OP_SIGMOID, OP_LOGIT, OP_LIKELIHOOD, OP_TF_PRIOR, OP_NORM_PRIOR, OP_COMPOSITE,
+    OP_POSTERIOR, OP_S2P, OP_S2P_PRIOR, OP_WAND, OP_COSINE
+};
+
+struct EwArgs {
+    const double *a, *b, *c, *d;
+    double *out;
+    int64_t n, out_stride;
+    bb25_params p;
+    double x0;
+    int flag;
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwArgs g) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += stride) {
+        double r;
+        if (OP == OP_SIGMOID) r = d_sigmoid(g.a[i]);
+        else if (OP == OP_LOGIT) r = d_logit(g.a[i]);
+        else if (OP == OP_LIKELIHOOD) r = d_sigmoid(g.p.alpha * (g.a[i] - g.p.beta));
+        else if (OP == OP_TF_PRIOR) r = d_tf_prior(g.a[i]);
+        else if (OP == OP_NORM_PRIOR) r = d_norm_prior(g.a[i]);
+        else if (OP == OP_COMPOSITE) r = d_composite_prior(g.a[i], g.b[i]);
+        else if (OP == OP_POSTERIOR) r = d_posterior(g.a[i], g.b[i], g.flag, g.x0);
+        else if (OP == OP_S2P) {
+            const double l = d_sigmoid(g.p.alpha * (g.a[i] - g.p.beta));
+            const double pr = g.p.prior_mode == 1 ? 0.5 : d_composite_prior(g.b[i], g.c[i]);
+            r = d_posterior(l, pr, g.p.has_base_rate, g.p.base_rate);
+        } else if (OP == OP_S2P_PRIOR) {
+            const double l = d_sigmoid(g.p.alpha * (g.a[i] - g.p.beta));
+            r = d_posterior(l, clamp_prob(g.d[i]), g.p.has_base_rate, g.p.base_rate);
+        } else if (OP == OP_WAND) {
+            const double l = d_sigmoid(g.p.alpha * (g.a[i] - g.p.beta));
+            r = d_posterior(l, g.x0, g.p.has_base_rate, g.p.base_rate);
+        } else {  // OP_COSINE, fusion.py:43-45
+            r = clamp_prob((1.0 + g.a[i]) / 2.0);
+        }
+        g.out[i * g.out_stride] = r;
+    }
+}
+
+template <int OP>
+static int run_ew(int device, EwArgs g, void *stream) {
+    if (g.n < 0 || !g.out || (g.n > 0 && !g.a)) { set_error("bad elementwise arguments"); return 1; }
+    if (g.n == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    int64_t blocks = (g.n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ew_kernel<OP><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+// fusion.py:119-169
+__device__ inline double d_gate(double x, int gating, double gb) {
+    switch (gating) {
+    case BB25_GATE_RELU: return x > 0.0 ? x : 0.0;
+    case BB25_GATE_SWISH: return x * d_sigmoid(gb * x);
+    case BB25_GATE_GELU: return x * d_sigmoid(1.702 * x);
+    case BB25_GATE_SOFTPLUS: {  // np.logaddexp(0, gb*x) / gb
+        const double y = gb * x;
+        return ((y > 0.0 ? y : 0.0) + log1p(exp(-fabs(y)))) / gb;
+    }
+    default: return x;
+    }
+}
+
+// fusion.py:243-280: one thread per row, signals summed left to right
+__global__ void __launch_bounds__(256) loc_kernel(const double *__restrict__ probs, int64_t m, int n,
+                                                  const double *__restrict__ w, double scale, int gating,
+                                                  double gb, int has_ml, double ml, double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        double acc = 0.0;
+        for (int j = 0; j < n; j++) {
+            double x = d_gate(d_logit(probs[i * n + j]), gating, gb);
+            if (has_ml) x = x < -ml ? -ml : (x > ml ? ml : x);
+            acc += w ? w[j] * x : x;
+        }
+        const double l = w ? scale * acc : (acc / (double)n) * scale;
+        out[i] = d_sigmoid(l);
+    }
+}
+
+// scorer.py:55-81: one thread per (term, block)
+__global__ void __launch_bounds__(256) blockmax_dense_kernel(const double *__restrict__ sm, int64_t n_terms,
+                                                             int64_t n_docs, int bs, int64_t nb,
+                                                             double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_terms * nb; i += stride) {
+        const int64_t t = i / nb, b = i % nb;
+        const int64_t s = b * bs, e = s + bs < n_docs ? s + bs : n_docs;
+        double mx = sm[t * n_docs + s];
+        for (int64_t d = s + 1; d < e; d++) {
+            const double v = sm[t * n_docs + d];
+            mx = v > mx ? v : mx;
+        }
+        out[i] = mx;
+    }
+}
+
+// block maxima of CSC columns; values are >= 0 so the fp32 bit pattern orders like
+// an unsigned integer and atomicMax applies
+__global__ void __launch_bounds__(256) blockmax_csc_kernel(const float *__restrict__ data,
+                                                           const int32_t *__restrict__ indices,
+                                                           const int64_t *__restrict__ indptr,
+                                                           const int32_t *__restrict__ terms, int n_terms,
+                                                           int64_t n_vocab, int bs, int64_t nb,
+                                                           unsigned int *__restrict__ out) {
+    for (int t = blockIdx.y; t < n_terms; t += gridDim.y) {
+        const int32_t term = terms[t];
+        if (term < 0 || term >= n_vocab) continue;
+        const int64_t s = indptr[term], e = indptr[term + 1];
+        for (int64_t j = s + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < e;
+             j += (int64_t)gridDim.x * blockDim.x)
+            atomicMax(&out[(int64_t)t * nb + indices[j] / bs], __float_as_uint(data[j]));
+    }
+}
+
+// ---- K7: merge S sorted [Q,k] lists --------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) merge_kernel(const int64_t *__restrict__ ids,
+                                                   const float *__restrict__ scores,
+                                                   const double *__restrict__ probs, int S, int64_t Q,
+                                                   int k, int P, int64_t *__restrict__ out_ids,
+                                                   float *__restrict__ out_scores,
+                                                   double *__restrict__ out_probs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
+    unsigned int *src = reinterpret_cast<unsigned int *>(smem + (size_t)P * 8);
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = S * k;
+    for (int i = tid; i < P; i += NT) {
+        if (i < n) {
+            const int s = i / k, r = i % k;
+            const int64_t o = ((int64_t)s * Q + q) * k + r;
+            // (score desc, global id asc); ids < 2^32
+            keys[i] = ((unsigned long long)__float_as_uint(scores[o]) << 32) |
+                      (unsigned long long)(0xFFFFFFFFu - (uint32_t)ids[o]);
+            src[i] = (unsigned int)i;
+        } else {
+            keys[i] = 0ull;
+            src[i] = 0xFFFFFFFFu;
+        }
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (P >> 1); t += NT) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = keys[lo], y = keys[hi];
+                // padding keys (src == ~0) must lose against real zero-score, id = 2^32-1 ... keys
+                const bool less = x < y || (x == y && src[lo] > src[hi]);
+                if (less == desc) {
+                    keys[lo] = y;
+                    keys[hi] = x;
+                    const unsigned int sx = src[lo];
+                    src[lo] = src[hi];
+                    src[hi] = sx;
+                }
+            }
+            __syncthreads();
+        }
+    for (int r = tid; r < k; r += NT) {
+        const unsigned int i = src[r];
+        const int s = i / k, rr = i % k;
+        const int64_t o = ((int64_t)s * Q + q) * k + rr;
+        out_ids[q * k + r] = ids[o];
+        if (out_scores) out_scores[q * k + r] = scores[o];
+        out_probs[q * k + r] = probs[o];
+    }
+}
+
+// ---- dense fp64 top-k: MSB-first radix select on (value bits desc, index asc) ---------
+// state: [0] prefix (value bits), [1] mask, [2] remaining, [3] idx prefix, [4] idx mask,
+//        [5] remaining among ties, [6] output cursor
+__global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const unsigned long long *state,
+                                 int shift, int bits, int phase, unsigned int *hist) {
+    __shared__ unsigned int sh[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = state[0], mask = state[1];
+    const unsigned long long iprefix = state[3], imask = state[4];
+    const unsigned int dm = (1u << bits) - 1u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+        if (phase == 0) {
+            if ((b & mask) == prefix) atomicAdd(&sh[(unsigned int)(b >> shift) & dm], 1u);
+        } else {
+            // ties on the threshold value: select the smallest indices (digit of ~index)
+            const unsigned long long inv = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
+            if (b == prefix && (inv & imask) == iprefix) atomicAdd(&sh[(unsigned int)(inv >> shift) & dm], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+__global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits, int phase, unsigned int *hist) {
+    if (threadIdx.x == 0) {
+        const int nb = 1 << bits;
+        unsigned long long rem = phase == 0 ? state[2] : state[5];
+        unsigned long long cum = 0;
+        int d = nb - 1;
+        for (; d > 0; d--) {
+            if (cum + hist[d] >= rem) break;
+            cum += hist[d];
+        }
+        rem -= cum;
+        const unsigned long long dm = (unsigned long long)(nb - 1);
+        if (phase == 0) {
+            state[0] |= (unsigned long long)d << shift;
+            state[1] |= dm << shift;
+            state[2] = rem;
+        } else {
+            state[3] |= (unsigned long long)d << shift;
+            state[4] |= dm << shift;
+            state[5] = rem;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+}
+
+__global__ void topk_begin_ties_kernel(unsigned long long *state) {
+    // after the value phase state[2] = how many elements equal to the threshold are needed
+    state[3] = 0;
+    state[4] = 0;
+    state[5] = state[2];
+    state[6] = 0;
+}
+
+// gather the k winners (unordered) as (value bits, ~index) pairs
+__global__ void topk_collect_kernel(const double *__restrict__ v, int64_t n, unsigned long long *state, int k,
+                                    unsigned long long *cand_bits, unsigned long long *cand_inv) {
+    const unsigned long long thr = state[0];
+    const unsigned long long ithr = state[3];  // smallest admissible ~index among ties
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+        const unsigned long long inv = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
+        if (b > thr || (b == thr && inv >= ithr)) {
+            const unsigned long long pos = atomicAdd(&state[6], 1ull);
+            if (pos < (unsigned long long)k) {
+                cand_bits[pos] = b;
+                cand_inv[pos] = inv;
+            }
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) topk_sort_kernel(const unsigned long long *cand_bits,
+                                                       const unsigned long long *cand_inv, int k, int P,
+                                                       int64_t *out_ids, double *out_vals) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *kb = reinterpret_cast<unsigned long long *>(smem);
+    unsigned long long *ki = kb + P;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P; i += NT) {
+        kb[i] = i < k ? cand_bits[i] : 0ull;
+        ki[i] = i < k ? cand_inv[i] : 0ull;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (P >> 1); t += NT) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long xb = kb[lo], yb = kb[hi], xi = ki[lo], yi = ki[hi];
+                const bool less = xb < yb || (xb == yb && xi < yi);
+                if (less == desc) {
+                    kb[lo] = yb; kb[hi] = xb;
+                    ki[lo] = yi; ki[hi] = xi;
+                }
+            }
+            __syncthreads();
+        }
+    for (int r = tid; r < k; r += NT) {
+        out_ids[r] = (int64_t)(0xFFFFFFFFFFFFFFFFull - ki[r]);
+        out_vals[r] = __longlong_as_double((long long)kb[r]);
+    }
+}
+
+}  // namespace bb25
+
+using namespace bb25;
+
+extern "C" {
+
+#define EW_BEGIN EwArgs g{}; g.out = out; g.n = n; g.out_stride = 1;
+
+int bb25_sigmoid(int device, const double *x, int64_t n, double *out, void *stream) {
+    EW_BEGIN g.a = x;
+    return run_ew<OP_SIGMOID>(device, g, stream);
+}
+int bb25_logit(int device, const double *p, int64_t n, double *out, void *stream) {
+    EW_BEGIN g.a = p;
+    return run_ew<OP_LOGIT>(device, g, stream);
+}
+int bb25_likelihood(int device, const bb25_params *p, const double *score, int64_t n, double *out, void *stream) {
+    if (!p) { set_error("params is NULL"); return 1; }
+    EW_BEGIN g.a = score; g.p = *p;
+    return run_ew<OP_LIKELIHOOD>(device, g, stream);
+}
+int bb25_tf_prior(int device, const double *tf, int64_t n, double *out, void *stream) {
+    EW_BEGIN g.a = tf;
+    return run_ew<OP_TF_PRIOR>(device, g, stream);
+}
+int bb25_norm_prior(int device, const double *ratio, int64_t n, double *out, void *stream) {
+    EW_BEGIN g.a = ratio;
+    return run_ew<OP_NORM_PRIOR>(device, g, stream);
+}
+int bb25_composite_prior(int device, const double *tf, const double *ratio, int64_t n, double *out, void *stream) {
+    if (n > 0 && !ratio) { set_error("ratio is NULL"); return 1; }
+    EW_BEGIN g.a = tf; g.b = ratio;
+    return run_ew<OP_COMPOSITE>(device, g, stream);
+}
+int bb25_posterior(int device, const double *lik, const double *prior, int has_base_rate, double base_rate,
+                   int64_t n, double *out, void *stream) {
+    if (n > 0 && !prior) { set_error("prior is NULL"); return 1; }
+    EW_BEGIN g.a = lik; g.b = prior; g.flag = has_base_rate; g.x0 = base_rate;
+    return run_ew<OP_POSTERIOR>(device, g, stream);
+}
+int bb25_score_to_probability(int device, const bb25_params *p, const double *score, const double *tf,
+                              const double *ratio, const double *prior, int64_t n, double *out,
+                              void *stream) {
+    if (!p) { set_error("params is NULL"); return 1; }
+    EW_BEGIN g.a = score; g.b = tf; g.c = ratio; g.d = prior; g.p = *p;
+    if (prior) return run_ew<OP_S2P_PRIOR>(device, g, stream);
+    if (p->prior_mode != 1 && n > 0 && (!tf || !ratio)) { set_error("tf / ratio is NULL"); return 1; }
+    return run_ew<OP_S2P>(device, g, stream);
+}
+int bb25_wand_upper_bound(int device, const bb25_params *p, const double *bm25_ub, double p_max, int64_t n,
+                          double *out, void *stream) {
+    if (!p) { set_error("params is NULL"); return 1; }
+    EW_BEGIN g.a = bm25_ub; g.p = *p; g.x0 = p_max;
+    return run_ew<OP_WAND>(device, g, stream);
+}
+int bb25_cosine_to_probability(int device, const double *cosv, int64_t n, double *out, int64_t out_stride,
+                               void *stream) {
+    if (out_stride < 1) { set_error("out_stride must be >= 1"); return 1; }
+    EW_BEGIN g.a = cosv; g.out_stride = out_stride;
+    return run_ew<OP_COSINE>(device, g, stream);
+}
+
+int bb25_log_odds_conjunction(int device, const double *probs, int64_t m, int n, const double *weights,
+                              double scale, int gating, double gating_beta, int has_max_logit,
+                              double max_logit, double *out, void *stream) {
+    if (m < 0 || n < 1 || !out || (m > 0 && !probs)) { set_error("bad log_odds_conjunction arguments"); return 1; }
+    if (gating < BB25_GATE_NONE || gating > BB25_GATE_SOFTPLUS) { set_error("unknown gating %d", gating); return 1; }
+    if (m == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    int64_t blocks = (m + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    loc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(probs, m, n, weights, scale, gating, gating_beta,
+                                                                  has_max_logit, max_logit, out);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_blockmax_dense(int device, const double *score_matrix, int64_t n_terms, int64_t n_docs,
+                        int block_size, double *out, void *stream) {
+    if (block_size < 1 || n_terms < 0 || n_docs < 1 || !score_matrix || !out) { set_error("bad blockmax arguments"); return 1; }
+    if (n_terms == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    const int64_t nb = (n_docs + block_size - 1) / block_size;
+    int64_t blocks = (n_terms * nb + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    blockmax_dense_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(score_matrix, n_terms, n_docs, block_size, nb, out);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_blockmax_csc(bb25_index *idx, const int32_t *terms, int n_terms, int block_size, float *out,
+                      void *stream) {
+    if (!idx || block_size < 1 || n_terms < 0 || !out || (n_terms > 0 && !terms)) { set_error("bad blockmax arguments"); return 1; }
+    if (n_terms == 0) return 0;
+    DeviceGuard dg(idx->device);
+    if (!dg.ok) { set_error("cannot select device"); return 1; }
+    const int64_t nb = (idx->n_docs + block_size - 1) / block_size;
+    cudaStream_t st = (cudaStream_t)stream;
+    BB25_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_terms * (size_t)nb, st));
+    dim3 grid(64, (unsigned)(n_terms < 1024 ? n_terms : 1024));
+    blockmax_csc_kernel<<<grid, 256, 0, st>>>(idx->data, idx->indices, idx->indptr, terms, n_terms, idx->n_vocab,
+                                              block_size, nb, reinterpret_cast<unsigned int *>(out));
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_merge_topk(int device, const int64_t *ids, const float *scores, const double *probs, int n_shards,
+                    int64_t n_queries, int k, int64_t *out_ids, float *out_scores, double *out_probs,
+                    void *stream) {
+    if (n_shards < 1 || n_queries < 0 || k < 1 || !ids || !scores || !probs || !out_ids || !out_probs) {
+        set_error("bad merge arguments");
+        return 1;
+    }
+    if ((int64_t)n_shards * k > 16384) { set_error("n_shards * k must be <= 16384"); return 1; }
+    if (n_queries == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    int P = 2;
+    while (P < n_shards * k) P <<= 1;
+    const size_t smem = (size_t)P * 12;
+    BB25_CUDA(cudaFuncSetAttribute(merge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
+    merge_kernel<512><<<(unsigned)n_queries, 512, smem, (cudaStream_t)stream>>>(ids, scores, probs, n_shards, n_queries, k, P,
+                                                                               out_ids, out_scores, out_probs);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_topk_f64(int device, const double *vals, int64_t n, int k, int64_t *out_ids, double *out_vals,
+                  void *stream) {
+    if (!vals || !out_ids || !out_vals || n < 1 || k < 1 || (int64_t)k > n || k > 8192) {
+        set_error("bad topk arguments (need 1 <= k <= min(n, 8192))");
+        return 1;
+    }
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *ws = nullptr;
+    const size_t o_hist = 64, o_cb = o_hist + 2048 * 4, o_ci = o_cb + (size_t)k * 8;
+    BB25_CUDA(cudaMallocAsync(&ws, o_ci + (size_t)k * 8, st));
+    unsigned long long *state = (unsigned long long *)ws;
+    unsigned int *hist = (unsigned int *)(ws + o_hist);
+    unsigned long long *cb = (unsigned long long *)(ws + o_cb), *ci = (unsigned long long *)(ws + o_ci);
+    int rc = 1;
+    do {
+        unsigned long long h_state[8] = {0, 0, (unsigned long long)k, 0, 0, 0, 0, 0};
+        if (cudaMemsetAsync(ws, 0, o_cb, st) != cudaSuccess) break;
+        if (cudaMemcpyAsync(state, h_state, sizeof(h_state), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;  // h_state is on the stack
+        int64_t blocks = (n + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        // value phase: 64 bits as 11,11,11,11,11,9
+        const int vshift[6] = {53, 42, 31, 20, 9, 0}, vbits[6] = {11, 11, 11, 11, 11, 9};
+        for (int p = 0; p < 6; p++) {
+            topk_hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(vals, n, state, vshift[p], vbits[p], 0, hist);
+            topk_scan_kernel<<<1, 256, 0, st>>>(state, vshift[p], vbits[p], 0, hist);
+            count_launch(2);
+        }
+        topk_begin_ties_kernel<<<1, 1, 0, st>>>(state);
+        count_launch();
+        // tie phase on ~index (64 bits, same digit plan)
+        for (int p = 0; p < 6; p++) {
+            topk_hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(vals, n, state, vshift[p], vbits[p], 1, hist);
+            topk_scan_kernel<<<1, 256, 0, st>>>(state, vshift[p], vbits[p], 1, hist);
+            count_launch(2);
+        }
+        topk_collect_kernel<<<(unsigned)blocks, 256, 0, st>>>(vals, n, state, k, cb, ci);
+        count_launch();
+        int P = 2;
+        while (P < k) P <<= 1;
+        if (cudaFuncSetAttribute(topk_sort_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16) != cudaSuccess) break;
+        topk_sort_kernel<512><<<1, 512, (size_t)P * 16, st>>>(cb, ci, k, P, out_ids, out_vals);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc) set_error("CUDA failure in bb25_topk_f64: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,327 @@
+// Index upload, per-(term, doc-tile) skip table, per-term k-th largest posting
+// value (threshold seeds), workspace management, error plumbing.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "bb25_internal.cuh"
+
+namespace bb25 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
+
+int ensure_workspace(bb25_index *idx, size_t bytes) {
+    if (bytes <= idx->ws_bytes) return 0;
+    if (idx->ws) {
+        BB25_CUDA(cudaDeviceSynchronize());
+        BB25_CUDA(cudaFree(idx->ws));
+        idx->ws = nullptr;
+        idx->ws_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 3);
+    BB25_CUDA(cudaMalloc(&idx->ws, want));
+    idx->ws_bytes = want;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// tile_off[t][b] = first posting of term t whose doc id >= b*tile_docs, relative to
+// indptr[t]; b in [0, n_tiles].  One thread per (t, b): binary search in the column.
+// ---------------------------------------------------------------------------------
+__global__ void build_tile_table_kernel(const int32_t *__restrict__ indices,
+                                        const int64_t *__restrict__ indptr, int64_t n_vocab,
+                                        int n_tiles, int tile_docs, uint32_t *__restrict__ tile_off) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = n_vocab * (int64_t)(n_tiles + 1);
+    if (gid >= total) return;
+    int64_t t = gid / (n_tiles + 1);
+    int b = (int)(gid % (n_tiles + 1));
+    int64_t s = indptr[t], e = indptr[t + 1];
+    int64_t target = (int64_t)b * tile_docs;
+    int64_t lo = s, hi = e;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)indices[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_off[gid] = (uint32_t)(lo - s);
+}
+
+// Input validation on device: column starts monotone, doc ids in range and strictly
+// ascending inside a column, posting values >= 0 and not NaN.  flags[0] |= bit.
+__global__ void validate_csc_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
+                                    const int64_t *__restrict__ indptr, int64_t n_vocab, int64_t n_docs,
+                                    int64_t nnz, int *flags) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    for (int64_t t = gid; t < n_vocab; t += stride) {
+        int64_t s = indptr[t], e = indptr[t + 1];
+        if (s > e || s < 0 || e > nnz) { bad |= 1; continue; }
+    }
+    if (gid == 0 && (indptr[0] != 0 || indptr[n_vocab] != nnz)) bad |= 1;
+    for (int64_t j = gid; j < nnz; j += stride) {
+        int32_t d = indices[j];
+        if (d < 0 || d >= n_docs) bad |= 2;
+        float v = data[j];
+        if (!(v >= 0.0f)) bad |= 4;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+// ascending check needs column boundaries: one thread per posting looks up whether
+// j is a column start through a boundary bitmap-free trick: compare with previous
+// posting and accept a decrease only where some column starts at j.
+__global__ void validate_sorted_kernel(const int32_t *__restrict__ indices,
+                                       const int64_t *__restrict__ indptr, int64_t n_vocab, int *flags) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_vocab; t += stride) {
+        int64_t s = indptr[t], e = indptr[t + 1];
+        // sample-free full check would be O(df) per thread; do it cooperatively below
+        // for long columns, here only for short ones
+        if (e - s <= 64)
+            for (int64_t j = s + 1; j < e; j++)
+                if (indices[j] <= indices[j - 1]) bad |= 8;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+__global__ void validate_sorted_long_kernel(const int32_t *__restrict__ indices,
+                                            const int64_t *__restrict__ indptr, int64_t n_vocab,
+                                            int *flags) {
+    // one block per term, only long columns
+    for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
+        int64_t s = indptr[t], e = indptr[t + 1];
+        if (e - s <= 64) continue;
+        int bad = 0;
+        for (int64_t j = s + 1 + threadIdx.x; j < e; j += blockDim.x)
+            if (indices[j] <= indices[j - 1]) bad = 8;
+        if (bad) atomicOr(flags, bad);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// kth[t] = k-th largest posting value of term t (0 when df < k): a valid lower bound
+// on the k-th best score of any query containing t, because posting values are >= 0
+// and fp32 addition of non-negative terms is monotone.  MSB-first radix select on the
+// fp32 bit pattern, one block per term, 4 passes of 8 bits.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kth_value_kernel(const float *__restrict__ data,
+                                                        const int64_t *__restrict__ indptr,
+                                                        int64_t n_vocab, int k, float *__restrict__ kth) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_mask, s_remaining;
+    for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
+        int64_t s = indptr[t], e = indptr[t + 1];
+        if (e - s < k) {
+            if (threadIdx.x == 0) kth[t] = 0.0f;
+            continue;
+        }
+        if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = (unsigned)k; }
+        __syncthreads();
+        for (int pass = 0; pass < 4; pass++) {
+            int shift = 24 - 8 * pass;
+            hist[threadIdx.x] = 0;
+            __syncthreads();
+            unsigned prefix = s_prefix, mask = s_mask;
+            // block-uniform trip count so the warp-wide match below is convergent
+            for (int64_t base = s; base < e; base += blockDim.x) {
+                int64_t j = base + threadIdx.x;
+                unsigned v = j < e ? __float_as_uint(data[j]) : 0u;
+                bool in = j < e && (v & mask) == prefix;
+                unsigned digit = (v >> shift) & 255u;
+                // warp-aggregate equal digits (values of one term cluster heavily)
+                unsigned key = in ? digit : 0xFFFFFFFFu;
+                unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+                if (in && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+                    atomicAdd(&hist[digit], (unsigned)__popc(peers));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned rem = s_remaining, cum = 0;
+                int d = 255;
+                for (; d > 0; d--) {
+                    if (cum + hist[d] >= rem) break;
+                    cum += hist[d];
+                }
+                s_remaining = rem - cum;
+                s_prefix = prefix | ((unsigned)d << shift);
+                s_mask = mask | (255u << shift);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) kth[t] = __uint_as_float(s_prefix);
+        __syncthreads();
+    }
+}
+
+int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out) {
+    auto it = idx->kth_cache.find(k);
+    if (it != idx->kth_cache.end()) {
+        *out = it->second;
+        return 0;
+    }
+    float *buf = nullptr;
+    BB25_CUDA(cudaMalloc(&buf, sizeof(float) * (size_t)idx->n_vocab));
+    idx->device_bytes += sizeof(float) * (size_t)idx->n_vocab;
+    int grid = (int)(idx->n_vocab < (int64_t)idx->sm_count * 8 ? idx->n_vocab : (int64_t)idx->sm_count * 8);
+    if (grid < 1) grid = 1;
+    kth_value_kernel<<<grid, 256, 0, st>>>(idx->data, idx->indptr, idx->n_vocab, k, buf);
+    BB25_LAUNCH_CHECK();
+    idx->kth_cache[k] = buf;
+    *out = buf;
+    return 0;
+}
+
+}  // namespace bb25
+
+using namespace bb25;
+
+extern "C" {
+
+const char *bb25_last_error(void) { return bb25::g_err; }
+int bb25_version(void) { return BB25_VERSION; }
+unsigned long long bb25_launch_count(void) { return bb25::g_launches.load(); }
+int bb25_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int pick_tile_docs() {
+    const char *e = getenv("BB25_TILE_DOCS");
+    if (e) {
+        int v = atoi(e);
+        if (v == 8192 || v == 16384 || v == 32768) return v;
+    }
+    return 16384;
+}
+
+int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, const float *data,
+                      const int32_t *indices, const int64_t *indptr, const int32_t *doc_len,
+                      double avgdl, int64_t doc_id_offset, bb25_index **out) {
+    if (!out) { set_error("out is NULL"); return 1; }
+    *out = nullptr;
+    if (n_docs < 1 || n_docs > (int64_t)kIdMask + 1) {
+        set_error("n_docs must be in [1, 2^29], got %lld", (long long)n_docs);
+        return 1;
+    }
+    if (n_vocab < 1 || nnz < 0 || !indptr || !doc_len || (nnz > 0 && (!data || !indices))) {
+        set_error("bad index arguments");
+        return 1;
+    }
+    if (!(avgdl > 0.0)) { set_error("avgdl must be > 0"); return 1; }
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+
+    bb25_index *idx = new bb25_index();
+    idx->device = device;
+    idx->n_docs = n_docs;
+    idx->n_vocab = n_vocab;
+    idx->nnz = nnz;
+    idx->avgdl = avgdl;
+    idx->doc_id_offset = doc_id_offset;
+    auto fail = [&]() { bb25_index_destroy(idx); return 1; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(); }
+    idx->sm_count = prop.multiProcessorCount;
+
+    size_t nn = (size_t)(nnz > 0 ? nnz : 1);
+#define TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return fail(); } } while (0)
+    TRY(cudaMalloc(&idx->data, nn * sizeof(float)));
+    TRY(cudaMalloc(&idx->indices, nn * sizeof(int32_t)));
+    TRY(cudaMalloc(&idx->indptr, (size_t)(n_vocab + 1) * sizeof(int64_t)));
+    TRY(cudaMalloc(&idx->doc_len, (size_t)n_docs * sizeof(int32_t)));
+    idx->device_bytes = nn * 8 + (size_t)(n_vocab + 1) * 8 + (size_t)n_docs * 4;
+    if (nnz > 0) {
+        TRY(cudaMemcpy(idx->data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault));
+        TRY(cudaMemcpy(idx->indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault));
+    }
+    TRY(cudaMemcpy(idx->indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyDefault));
+    TRY(cudaMemcpy(idx->doc_len, doc_len, (size_t)n_docs * sizeof(int32_t), cudaMemcpyDefault));
+    TRY(cudaMallocHost(&idx->pinned, 4096));
+
+    // validate
+    int *flags = nullptr;
+    TRY(cudaMalloc(&flags, sizeof(int)));
+    TRY(cudaMemset(flags, 0, sizeof(int)));
+    validate_csc_kernel<<<idx->sm_count * 4, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, n_docs, nnz, flags);
+    count_launch();
+    int hflags = 0;
+    TRY(cudaMemcpy(&hflags, flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (hflags == 0) {
+        validate_sorted_kernel<<<idx->sm_count * 4, 256>>>(idx->indices, idx->indptr, n_vocab, flags);
+        validate_sorted_long_kernel<<<idx->sm_count * 4, 256>>>(idx->indices, idx->indptr, n_vocab, flags);
+        count_launch(2);
+        TRY(cudaMemcpy(&hflags, flags, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(flags);
+    if (hflags) {
+        set_error("invalid CSC input (flags=%d: 1 indptr, 2 doc id out of range, 4 negative/NaN value, 8 doc ids not ascending)", hflags);
+        return fail();
+    }
+
+    idx->tile_docs = pick_tile_docs();
+    idx->n_tiles = (int)((n_docs + idx->tile_docs - 1) / idx->tile_docs);
+    size_t tt = (size_t)n_vocab * (size_t)(idx->n_tiles + 1);
+    TRY(cudaMalloc(&idx->tile_off, tt * sizeof(uint32_t)));
+    idx->device_bytes += tt * sizeof(uint32_t);
+    {
+        int64_t blocks = (int64_t)((tt + 255) / 256);
+        build_tile_table_kernel<<<(unsigned)blocks, 256>>>(idx->indices, idx->indptr, n_vocab, idx->n_tiles,
+                                                          idx->tile_docs, idx->tile_off);
+        count_launch();
+        TRY(cudaGetLastError());
+        TRY(cudaDeviceSynchronize());
+    }
+#undef TRY
+    *out = idx;
+    return 0;
+}
+
+void bb25_index_destroy(bb25_index *idx) {
+    if (!idx) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(idx->device);
+    cudaFree(idx->data);
+    cudaFree(idx->indices);
+    cudaFree(idx->indptr);
+    cudaFree(idx->doc_len);
+    cudaFree(idx->tile_off);
+    for (auto &kv : idx->kth_cache) cudaFree(kv.second);
+    if (idx->ws) cudaFree(idx->ws);
+    if (idx->pinned) cudaFreeHost(idx->pinned);
+    for (int i = 0; i < idx->n_ev; i++) cudaEventDestroy(idx->ev[i]);
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+    delete idx;
+}
+
+int bb25_index_info(const bb25_index *idx, int64_t *n_docs, int64_t *n_vocab, int64_t *nnz,
+                    int *tile_docs, int *n_tiles, int64_t *device_bytes) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (n_docs) *n_docs = idx->n_docs;
+    if (n_vocab) *n_vocab = idx->n_vocab;
+    if (nnz) *nnz = idx->nnz;
+    if (tile_docs) *tile_docs = idx->tile_docs;
+    if (n_tiles) *n_tiles = idx->n_tiles;
+    if (device_bytes) *device_bytes = (int64_t)(idx->device_bytes + idx->ws_bytes);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// Internal declarations shared by the libbb25.so translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/bb25.h"
+
+namespace bb25 {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define BB25_CUDA(expr)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            bb25::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                            __FILE__, __LINE__);                                     \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+#define BB25_LAUNCH_CHECK()                                                          \
+    do {                                                                             \
+        bb25::count_launch();                                                        \
+        cudaError_t _e = cudaGetLastError();                                         \
+        if (_e != cudaSuccess) {                                                     \
+            bb25::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                     \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+// RAII device switch
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr double kEps = 1e-10;  // probability.py:20
+
+// ---- probability.py / fusion.py scalar math, fp64 -------------------------------
+__host__ __device__ inline double clamp_prob(double p) {  // probability.py:24-26
+    return p < kEps ? kEps : (p > 1.0 - kEps ? 1.0 - kEps : p);
+}
+__device__ inline double d_sigmoid(double x) {  // probability.py:29-41 (split form)
+    if (x >= 0.0) return 1.0 / (1.0 + exp(-x));
+    double e = exp(x);
+    return e / (1.0 + e);
+}
+__device__ inline double d_logit(double p) {  // probability.py:44-48
+    p = clamp_prob(p);
+    return log(p / (1.0 - p));
+}
+__device__ inline double d_tf_prior(double tf) {  // probability.py:110-115
+    return 0.2 + 0.7 * fmin(1.0, tf / 10.0);
+}
+__device__ inline double d_norm_prior(double r) {  // probability.py:117-129
+    return 0.3 + 0.6 * (1.0 - fmin(1.0, fabs(r - 0.5) * 2.0));
+}
+__device__ inline double d_composite_prior(double tf, double r) {  // probability.py:131-140
+    double v = 0.7 * d_tf_prior(tf) + 0.3 * d_norm_prior(r);
+    return v < 0.1 ? 0.1 : (v > 0.9 ? 0.9 : v);
+}
+__device__ inline double d_posterior(double l, double p, int has_br, double br) {  // :142-169
+    double num = l * p;
+    double den = num + (1.0 - l) * (1.0 - p);
+    double x = clamp_prob(num / den);
+    if (has_br) {
+        double nb = x * br;
+        double db = nb + (1.0 - x) * (1.0 - br);
+        x = clamp_prob(nb / db);
+    }
+    return x;
+}
+// scorer.py:618-638 for one document: 0.0 unless score > 0
+__device__ inline double d_doc_probability(const bb25_params &p, float score, int tf, int doc_len,
+                                           double avgdl) {
+    if (!(score > 0.0f)) return 0.0;
+    double l = d_sigmoid(p.alpha * ((double)score - p.beta));
+    double prior = p.prior_mode == 1 ? 0.5 : d_composite_prior((double)tf, (double)doc_len / avgdl);
+    return d_posterior(l, prior, p.has_base_rate, p.base_rate);
+}
+
+// ---- candidate key: score desc, then local doc id asc ----------------------------
+// [63:33] fp32 score bits (scores are >= 0 so bit 31 is clear)
+// [32:4]  0x1FFFFFFF - local doc id   (n_docs <= 2^29 per index)
+// [3:0]   matched-term count, saturated at 15 (the tf prior saturates at 10)
+constexpr uint32_t kIdMask = 0x1FFFFFFFu;
+__host__ __device__ inline unsigned long long make_key(uint32_t score_bits, uint32_t local_id,
+                                                       uint32_t tf) {
+    return ((unsigned long long)score_bits << 33) |
+           ((unsigned long long)(kIdMask - local_id) << 4) | (unsigned long long)(tf > 15u ? 15u : tf);
+}
+__host__ __device__ inline uint32_t key_score_bits(unsigned long long k) { return (uint32_t)(k >> 33); }
+__host__ __device__ inline uint32_t key_local_id(unsigned long long k) {
+    return kIdMask - (uint32_t)((k >> 4) & kIdMask);
+}
+__host__ __device__ inline uint32_t key_tf(unsigned long long k) { return (uint32_t)(k & 15ull); }
+
+}  // namespace bb25
+
+struct bb25_index {
+    int device = 0;
+    int sm_count = 0;
+    int64_t n_docs = 0, n_vocab = 0, nnz = 0, doc_id_offset = 0;
+    double avgdl = 0.0;
+    float *data = nullptr;
+    int32_t *indices = nullptr;
+    int64_t *indptr = nullptr;
+    int32_t *doc_len = nullptr;
+    int tile_docs = 0;  // docs per traversal tile (shared-memory accumulator span)
+    int n_tiles = 0;
+    uint32_t *tile_off = nullptr;  // [n_vocab][n_tiles+1] offsets relative to indptr[t]
+    std::map<int, float *> kth_cache;  // k -> fp32[n_vocab] k-th largest posting value per term
+    // grow-only device workspace shared by query calls (serialised by mu)
+    std::mutex mu;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    void *pinned = nullptr;  // small pinned host scratch
+    size_t device_bytes = 0;
+    // stats of the last retrieve_batch
+    int64_t st_launches = 0, st_passes = 0, st_reruns = 0, st_candidates = 0;
+    // CUDA-event pairs around the traversal launches of the last retrieve_batch
+    static constexpr int kMaxEv = 256;
+    cudaEvent_t ev[2 * kMaxEv] = {};
+    int n_ev = 0;       // events created so far
+    int ev_used = 0;    // pairs recorded in the last call
+    double st_traverse_ms = 0.0;
+    int64_t st_traverse_launches = 0;
+};
+
+namespace bb25 {
+int ensure_workspace(bb25_index *idx, size_t bytes);
+int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out);
+}  // namespace bb25

@@ -1,0 +1,800 @@
+// Posting-list traversal (K1/K2), fused posterior epilogue (K3), threshold-driven
+// candidate emission and per-query selection (K4).
+//
+// Layout of the work: the document space of a shard is cut into tiles of
+// `tile_docs` documents.  One CTA owns one tile at a time: fp32 score accumulators
+// and 8-bit matched-term counters for the tile live in shared memory, the CTA walks
+// the (query, term) list of a chunk of queries, and for every term streams the slice
+// of the posting list that falls inside the tile (located through the per-(term,tile)
+// skip table) with 128-bit loads and adds it into the accumulators.  Terms of one
+// query are applied in query order with a block barrier between them, so every
+// document's fp32 sum is formed in exactly the order bm25s forms it (bit-exact).
+// Work items are handed out tile-major through a global counter, so all CTAs work on
+// the same one or two tiles for different queries and the tile's slice of the index
+// is served from L2 after its first touch.
+#include <algorithm>
+
+#include "bb25_internal.cuh"
+
+namespace bb25 {
+
+constexpr int QB = 8;      // queries per work item
+constexpr int MAXT = 128;  // (query, term) occurrences staged per metadata batch
+constexpr int kMaxK = 4096;
+
+enum { MODE_RETRIEVE = 0, MODE_SCORES = 1, MODE_PROBS = 2 };
+
+struct TileArgs {
+    const float *data;
+    const int32_t *indices;
+    const int64_t *indptr;
+    const uint32_t *tile_off;
+    const int32_t *doc_len;
+    double avgdl;
+    int n_tiles;
+    int64_t n_docs;
+    const int32_t *q_terms;    // sanitised copy, indexed by absolute position - term_base
+    const uint8_t *q_nocount;  // 1 = duplicate occurrence: add the score, do not count
+    const int64_t *q_off;
+    int64_t term_base;
+    const int32_t *q_list;  // NULL = queries [0, n_q)
+    int n_q;
+    int tile_begin, tile_end;
+    const unsigned long long *thr;
+    unsigned int *cand_cnt;
+    unsigned long long *cand_key;
+    int cap;
+    float *out_scores;
+    double *out_probs;
+    int64_t out_stride;
+    bb25_params params;
+    unsigned long long *work_counter;
+};
+
+struct TileMeta {
+    long long m_start[MAXT];
+    unsigned long long s_thr[QB];
+    long long s_t0[QB];
+    long long item;
+    uint32_t m_len[MAXT];
+    int s_q[QB];
+    int s_m[QB];
+    int s_pre[QB + 1];
+    uint8_t m_flags[MAXT];
+    uint8_t m_slot[MAXT];
+};
+
+__device__ __forceinline__ int4 ld_nc_i4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_nc_f4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void rmw1(float *acc, uint8_t *cnt, int off, float v) {
+    acc[off] = __fadd_rn(acc[off], v);
+    if (COUNT) {
+        unsigned c = cnt[off];
+        cnt[off] = (uint8_t)(c < 255u ? c + 1u : 255u);
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void apply4(float *acc, uint8_t *cnt, const int4 &d, const float4 &v,
+                                       int doc_base) {
+    rmw1<COUNT>(acc, cnt, d.x - doc_base, v.x);
+    rmw1<COUNT>(acc, cnt, d.y - doc_base, v.y);
+    rmw1<COUNT>(acc, cnt, d.z - doc_base, v.z);
+    rmw1<COUNT>(acc, cnt, d.w - doc_base, v.w);
+}
+
+// Add postings [s, s+len) of one term into the tile accumulators.  Doc ids inside a
+// posting list are distinct, so no two threads touch the same accumulator.
+template <int NT, bool COUNT>
+__device__ __forceinline__ void scatter_slice(const float *__restrict__ data,
+                                              const int32_t *__restrict__ indices, long long s,
+                                              uint32_t len, float *acc, uint8_t *cnt, int doc_base,
+                                              int tid) {
+    const long long e = s + (long long)len;
+    long long a0 = (s + 3) & ~3ll;  // first 16-byte aligned element
+    if (a0 > e) a0 = e;
+    if (tid < (int)(a0 - s)) {
+        long long j = s + tid;
+        rmw1<COUNT>(acc, cnt, indices[j] - doc_base, data[j]);
+    }
+    const int n4 = (int)((e - a0) >> 2);
+    const int4 *idx4 = reinterpret_cast<const int4 *>(indices + a0);
+    const float4 *val4 = reinterpret_cast<const float4 *>(data + a0);
+    for (int g = tid; g < n4; g += 2 * NT) {
+        int4 d0 = ld_nc_i4(idx4 + g);
+        float4 v0 = ld_nc_f4(val4 + g);
+        const bool two = (g + NT) < n4;
+        int4 d1 = d0;
+        float4 v1 = v0;
+        if (two) {
+            d1 = ld_nc_i4(idx4 + g + NT);
+            v1 = ld_nc_f4(val4 + g + NT);
+        }
+        apply4<COUNT>(acc, cnt, d0, v0, doc_base);
+        if (two) apply4<COUNT>(acc, cnt, d1, v1, doc_base);
+    }
+    const long long t0 = a0 + ((long long)n4 << 2);
+    if (t0 + tid < e) {
+        long long j = t0 + tid;
+        rmw1<COUNT>(acc, cnt, indices[j] - doc_base, data[j]);
+    }
+}
+
+template <int D, int NT, int MODE>
+__global__ void __launch_bounds__(NT, (D <= 16384) ? 2 : 1) tile_kernel(const __grid_constant__ TileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *acc = reinterpret_cast<float *>(smem);
+    uint8_t *cnt = smem + (size_t)D * 4;
+    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + (size_t)D * 5);
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < D / 4; i += NT) reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < D / 16; i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
+
+    const int n_chunks = (a.n_q + QB - 1) / QB;
+    const long long n_items = (long long)(a.tile_end - a.tile_begin) * n_chunks;
+
+    for (;;) {
+        __syncthreads();  // previous item fully consumed (also covers the zero-fill above)
+        if (tid == 0) meta->item = (long long)atomicAdd(a.work_counter, 1ull);
+        __syncthreads();
+        const long long item = meta->item;
+        if (item >= n_items) break;
+        const int tile = a.tile_begin + (int)(item / n_chunks);
+        const int slot0 = (int)(item % n_chunks) * QB;
+        const int nslots = min(QB, a.n_q - slot0);
+        const int doc_base = tile * D;
+
+        if (tid < nslots) {
+            const int q = a.q_list ? a.q_list[slot0 + tid] : slot0 + tid;
+            const long long t0 = a.q_off[q];
+            meta->s_q[tid] = q;
+            meta->s_t0[tid] = t0;
+            meta->s_m[tid] = (int)max(0ll, (long long)a.q_off[q + 1] - t0);
+            if (MODE == MODE_RETRIEVE) meta->s_thr[tid] = a.thr[q];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int p = 0;
+            for (int i = 0; i < nslots; i++) {
+                meta->s_pre[i] = p;
+                p += meta->s_m[i];
+            }
+            meta->s_pre[nslots] = p;
+        }
+        __syncthreads();
+        const int total = meta->s_pre[nslots];
+
+        for (int b0 = 0; b0 < total; b0 += MAXT) {
+            const int nb = min(MAXT, total - b0);
+            if (tid < nb) {
+                const int j = b0 + tid;
+                int slot = 0;
+                while (j >= meta->s_pre[slot + 1]) slot++;
+                const long long pos = meta->s_t0[slot] + (j - meta->s_pre[slot]) - a.term_base;
+                const int t = a.q_terms[pos];
+                const uint32_t *to = a.tile_off + (size_t)t * (size_t)(a.n_tiles + 1) + tile;
+                const uint32_t lo = to[0], hi = to[1];
+                meta->m_start[tid] = a.indptr[t] + (long long)lo;
+                meta->m_len[tid] = hi - lo;
+                meta->m_flags[tid] = (uint8_t)((a.q_nocount[pos] ? 1 : 0) | ((j == meta->s_pre[slot + 1] - 1) ? 2 : 0));
+                meta->m_slot[tid] = (uint8_t)slot;
+            }
+            __syncthreads();
+            for (int i = 0; i < nb; i++) {
+                const long long s = meta->m_start[i];
+                const uint32_t len = meta->m_len[i];
+                const int flags = meta->m_flags[i];
+                if (len) {
+                    if (flags & 1) scatter_slice<NT, false>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                    else scatter_slice<NT, true>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                }
+                __syncthreads();
+                if (flags & 2) {
+                    // ---- last term of this query: fused epilogue over the tile ----
+                    const int slot = meta->m_slot[i];
+                    if (MODE == MODE_RETRIEVE) {
+                        const int q = meta->s_q[slot];
+                        const unsigned long long thr = meta->s_thr[slot];
+                        const uint32_t thr_score = (uint32_t)(thr >> 33);
+                        unsigned int *ccnt = a.cand_cnt + q;
+                        unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
+                        float4 *acc4 = reinterpret_cast<float4 *>(acc);
+                        uint32_t *cnt4 = reinterpret_cast<uint32_t *>(cnt);
+                        for (int w = tid; w < D / 4; w += NT) {
+                            const uint32_t c4 = cnt4[w];
+                            if (c4 == 0) continue;  // untouched quad
+                            const float4 v = acc4[w];
+                            acc4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            cnt4[w] = 0;
+                            const float av[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const uint32_t bits = __float_as_uint(av[c]);
+                                if (bits != 0u && bits >= thr_score) {
+                                    const unsigned long long key =
+                                        make_key(bits, (uint32_t)(doc_base + w * 4 + c), (c4 >> (8 * c)) & 255u);
+                                    if (key >= thr) {
+                                        const unsigned int pos = atomicAdd(ccnt, 1u);
+                                        if (pos < (unsigned)a.cap) crow[pos] = key;
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        for (int w = tid; w < D; w += NT) {
+                            const long long d = (long long)doc_base + w;
+                            const float sc = acc[w];
+                            const int c = cnt[w];
+                            acc[w] = 0.f;
+                            cnt[w] = 0;
+                            if (d < a.n_docs) {
+                                if (MODE == MODE_SCORES) a.out_scores[d] = sc;
+                                else a.out_probs[d * a.out_stride] = d_doc_probability(a.params, sc, c, a.doc_len[d], a.avgdl);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// per-query preparation: sanitised term copy, duplicate flags, threshold seed
+// ---------------------------------------------------------------------------------
+__global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const int64_t *__restrict__ q_off,
+                                    int64_t n_q, int64_t term_base, int64_t n_vocab,
+                                    const float *__restrict__ kth, int32_t *__restrict__ qt_ws,
+                                    uint8_t *__restrict__ nocount, unsigned long long *__restrict__ thr,
+                                    unsigned int *__restrict__ cand_cnt, unsigned int *__restrict__ n_prev,
+                                    int *err) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_q) return;
+    const int64_t t0 = q_off[q], t1 = q_off[q + 1];
+    if (t1 < t0) { atomicOr(err, 2); }
+    uint32_t best = 0;
+    for (int64_t i = t0; i < t1; i++) {
+        int32_t t = q_terms[i];
+        if (t < 0 || (int64_t)t >= n_vocab) {
+            atomicOr(err, 1);
+            t = 0;
+        }
+        bool dup = false;
+        for (int64_t j = t0; j < i && !dup; j++) dup = (q_terms[j] == t);
+        qt_ws[i - term_base] = t;
+        nocount[i - term_base] = dup ? 1 : 0;
+        if (kth) {
+            uint32_t b = __float_as_uint(kth[t]);
+            best = b > best ? b : best;
+        }
+    }
+    if (thr) {
+        thr[q] = (unsigned long long)best << 33;
+        cand_cnt[q] = 0;
+        n_prev[q] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// per-query selection: sort the candidate keys (descending), then either tighten the
+// threshold (overflow / intermediate group) or write the final top-k.
+// ---------------------------------------------------------------------------------
+struct SelectArgs {
+    const int32_t *q_list;
+    unsigned int *cand_cnt;
+    unsigned int *n_prev;
+    unsigned long long *cand_key;
+    unsigned long long *thr;
+    int cap, k, final_pass;
+    unsigned int *n_over;
+    int32_t *over_list;
+    const int32_t *doc_len;
+    double avgdl;
+    int64_t n_docs, doc_id_offset;
+    bb25_params params;
+    int64_t *out_ids;
+    float *out_scores;
+    double *out_probs;
+    unsigned long long *n_cand_total;
+};
+
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int P, int tid) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (P >> 1); t += NT) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = keys[lo], y = keys[hi];
+                if ((x < y) == desc) {
+                    keys[lo] = y;
+                    keys[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ SelectArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
+    uint8_t *flag = smem + (size_t)a.cap * 8;
+    const int tid = threadIdx.x;
+    const int q = a.q_list ? a.q_list[blockIdx.x] : (int)blockIdx.x;
+    const unsigned int n_raw = a.cand_cnt[q];
+    const int n = (int)min(n_raw, (unsigned)a.cap);
+    unsigned long long *row = a.cand_key + (size_t)q * (size_t)a.cap;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += NT) keys[i] = i < n ? row[i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc<NT>(keys, P, tid);
+    const int k = a.k;
+
+    if (n_raw > (unsigned)a.cap) {
+        // more candidates than the row holds: the k-th best of the stored ones is a
+        // valid, strictly tighter bound; redo this tile group for this query
+        if (tid == 0) {
+            a.thr[q] = keys[k - 1] & ~15ull;
+            a.cand_cnt[q] = a.n_prev[q];
+            const unsigned int pos = atomicAdd(a.n_over, 1u);
+            a.over_list[pos] = q;
+        }
+        return;
+    }
+    if (!a.final_pass) {
+        const int keep = min(n, k);
+        for (int i = tid; i < keep; i += NT) row[i] = keys[i];
+        if (tid == 0) {
+            a.cand_cnt[q] = keep;
+            a.n_prev[q] = keep;
+            if (n >= k) {
+                const unsigned long long t = keys[k - 1] & ~15ull;
+                if (t > a.thr[q]) a.thr[q] = t;
+            }
+        }
+        return;
+    }
+    const int n_pos = min(n, k);
+    if (tid == 0 && a.n_cand_total) atomicAdd(a.n_cand_total, (unsigned long long)n);
+    for (int r = tid; r < n_pos; r += NT) {
+        const unsigned long long key = keys[r];
+        const uint32_t id = key_local_id(key);
+        const float sc = __uint_as_float(key_score_bits(key));
+        const size_t o = (size_t)q * (size_t)k + r;
+        a.out_ids[o] = (int64_t)id + a.doc_id_offset;
+        if (a.out_scores) a.out_scores[o] = sc;
+        a.out_probs[o] = d_doc_probability(a.params, sc, (int)key_tf(key), a.doc_len[id], a.avgdl);
+    }
+    if (n_pos < k) {
+        // fewer than k matching documents: bm25s fills the tail with zero-score
+        // documents; canonically the lowest doc ids not already listed.  At most
+        // n_pos < k ids are taken, so the fill ids all lie in [0, k).
+        for (int i = tid; i < k; i += NT) flag[i] = 0;
+        __syncthreads();
+        for (int r = tid; r < n_pos; r += NT) {
+            const uint32_t id = key_local_id(keys[r]);
+            if (id < (uint32_t)k) flag[id] = 1;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int r = n_pos;
+            for (int base = 0; base < k && r < k; base += 32) {
+                const int id = base + tid;
+                const bool free_id = id < k && (int64_t)id < a.n_docs && !flag[id];
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, free_id);
+                const int my = r + __popc(m & ((1u << tid) - 1u));
+                if (free_id && my < k) {
+                    const size_t o = (size_t)q * (size_t)k + my;
+                    a.out_ids[o] = (int64_t)id + a.doc_id_offset;
+                    if (a.out_scores) a.out_scores[o] = 0.0f;
+                    a.out_probs[o] = 0.0;
+                }
+                r += __popc(m);
+            }
+        }
+    }
+}
+
+__global__ void fill_strided_f64_kernel(double *out, int64_t n, int64_t stride, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i * stride] = v;
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+template <int MODE>
+static int launch_tile(const bb25_index *idx, const TileArgs &a, cudaStream_t st) {
+    const int n_chunks = (a.n_q + QB - 1) / QB;
+    const long long n_items = (long long)(a.tile_end - a.tile_begin) * n_chunks;
+    if (n_items <= 0) return 0;
+    BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+#define BB25_TILE_CASE(DV, NTV)                                                                     \
+    {                                                                                               \
+        const size_t smem = (size_t)DV * 5 + sizeof(TileMeta);                                      \
+        BB25_CUDA(cudaFuncSetAttribute(tile_kernel<DV, NTV, MODE>,                                  \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        const int per_sm = (DV <= 16384) ? 2 : 1;                                                   \
+        long long grid = (long long)idx->sm_count * per_sm;                                         \
+        if (grid > n_items) grid = n_items;                                                         \
+        tile_kernel<DV, NTV, MODE><<<(unsigned)grid, NTV, smem, st>>>(a);                           \
+    }
+    switch (idx->tile_docs) {
+    case 8192: BB25_TILE_CASE(8192, 256) break;
+    case 16384: BB25_TILE_CASE(16384, 512) break;
+    case 32768: BB25_TILE_CASE(32768, 1024) break;
+    default: set_error("unsupported tile size %d", idx->tile_docs); return 1;
+    }
+#undef BB25_TILE_CASE
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+static void base_args(const bb25_index *idx, TileArgs &a) {
+    a.data = idx->data;
+    a.indices = idx->indices;
+    a.indptr = idx->indptr;
+    a.tile_off = idx->tile_off;
+    a.doc_len = idx->doc_len;
+    a.avgdl = idx->avgdl;
+    a.n_tiles = idx->n_tiles;
+    a.n_docs = idx->n_docs;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// dense single-query outputs (get_scores / get_probabilities)
+static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const int32_t *q_terms_host,
+                     int n_terms, float *out_scores, double *out_probs, int64_t out_stride,
+                     cudaStream_t st) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (n_terms < 0 || (n_terms > 0 && !q_terms_host)) { set_error("bad query"); return 1; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("cannot select device"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    for (int i = 0; i < n_terms; i++)
+        if (q_terms_host[i] < 0 || q_terms_host[i] >= idx->n_vocab) {
+            set_error("query term id %d out of range [0, %lld)", q_terms_host[i], (long long)idx->n_vocab);
+            return 1;
+        }
+    if (n_terms == 0) {
+        if (mode == MODE_SCORES) {
+            BB25_CUDA(cudaMemsetAsync(out_scores, 0, sizeof(float) * (size_t)idx->n_docs, st));
+        } else {
+            fill_strided_f64_kernel<<<(unsigned)((idx->n_docs + 255) / 256), 256, 0, st>>>(out_probs, idx->n_docs, out_stride, 0.0);
+            BB25_LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    const size_t o_terms = 0;
+    const size_t o_nc = align_up(o_terms + sizeof(int32_t) * (size_t)n_terms);
+    const size_t o_qoff = align_up(o_nc + (size_t)n_terms);
+    const size_t o_src = align_up(o_qoff + 2 * sizeof(int64_t));
+    const size_t o_ctr = align_up(o_src + sizeof(int32_t) * (size_t)n_terms);
+    const size_t o_err = align_up(o_ctr + sizeof(unsigned long long));
+    const size_t total = align_up(o_err + sizeof(int));
+    if (ensure_workspace(idx, total)) return 1;
+    unsigned char *ws = (unsigned char *)idx->ws;
+    int32_t *d_terms = (int32_t *)(ws + o_terms);
+    uint8_t *d_nc = ws + o_nc;
+    int64_t *d_qoff = (int64_t *)(ws + o_qoff);
+    int32_t *d_src = (int32_t *)(ws + o_src);
+    int *d_err = (int *)(ws + o_err);
+    int64_t hq[2] = {0, n_terms};
+    BB25_CUDA(cudaMemcpyAsync(d_src, q_terms_host, sizeof(int32_t) * (size_t)n_terms, cudaMemcpyHostToDevice, st));
+    BB25_CUDA(cudaMemcpyAsync(d_qoff, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
+    BB25_CUDA(cudaStreamSynchronize(st));  // hq / q_terms_host are pageable stack/user memory
+    BB25_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    prep_queries_kernel<<<1, 32, 0, st>>>(d_src, d_qoff, 1, 0, idx->n_vocab, nullptr, d_terms, d_nc, nullptr, nullptr, nullptr, d_err);
+    BB25_LAUNCH_CHECK();
+    TileArgs a{};
+    base_args(idx, a);
+    a.q_terms = d_terms;
+    a.q_nocount = d_nc;
+    a.q_off = d_qoff;
+    a.term_base = 0;
+    a.q_list = nullptr;
+    a.n_q = 1;
+    a.tile_begin = 0;
+    a.tile_end = idx->n_tiles;
+    a.out_scores = out_scores;
+    a.out_probs = out_probs;
+    a.out_stride = out_stride;
+    if (params) a.params = *params;
+    a.work_counter = (unsigned long long *)(ws + o_ctr);
+    if (mode == MODE_SCORES) return launch_tile<MODE_SCORES>(idx, a, st);
+    return launch_tile<MODE_PROBS>(idx, a, st);
+}
+
+static int check_params(const bb25_params *p) {
+    if (!p) { set_error("params is NULL"); return 1; }
+    if (p->has_base_rate && !(p->base_rate > 0.0 && p->base_rate < 1.0)) {
+        set_error("base_rate must be in (0, 1), got %g", p->base_rate);
+        return 1;
+    }
+    if (p->prior_mode != 0 && p->prior_mode != 1) { set_error("prior_mode must be 0 or 1"); return 1; }
+    return 0;
+}
+
+static int retrieve_device(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                           const int64_t *q_off, int64_t n_q, int64_t term_base, int64_t n_terms_total,
+                           int k, int64_t *out_ids, float *out_scores, double *out_probs,
+                           cudaStream_t st) {
+    // caller holds idx->mu and the device guard
+    int cap = 1024;
+    while (cap < 8 * k && cap < 16384) cap <<= 1;
+    const size_t nt = (size_t)(n_terms_total > 0 ? n_terms_total : 1);
+    const size_t o_terms = 0;
+    const size_t o_nc = align_up(o_terms + sizeof(int32_t) * nt);
+    const size_t o_thr = align_up(o_nc + nt);
+    const size_t o_cnt = align_up(o_thr + sizeof(unsigned long long) * (size_t)n_q);
+    const size_t o_prev = align_up(o_cnt + sizeof(unsigned int) * (size_t)n_q);
+    const size_t o_la = align_up(o_prev + sizeof(unsigned int) * (size_t)n_q);
+    const size_t o_lb = align_up(o_la + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_ctr = align_up(o_lb + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_key = align_up(o_ctr + 64);
+    const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
+    if (ensure_workspace(idx, total)) return 1;
+    unsigned char *ws = (unsigned char *)idx->ws;
+    int32_t *d_terms = (int32_t *)(ws + o_terms);
+    uint8_t *d_nc = ws + o_nc;
+    unsigned long long *d_thr = (unsigned long long *)(ws + o_thr);
+    unsigned int *d_cnt = (unsigned int *)(ws + o_cnt);
+    unsigned int *d_prev = (unsigned int *)(ws + o_prev);
+    int32_t *d_list[2] = {(int32_t *)(ws + o_la), (int32_t *)(ws + o_lb)};
+    unsigned long long *d_work = (unsigned long long *)(ws + o_ctr);
+    unsigned int *d_nover = (unsigned int *)(ws + o_ctr + 8);
+    int *d_err = (int *)(ws + o_ctr + 16);
+    unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
+    unsigned long long *d_keys = (unsigned long long *)(ws + o_key);
+
+    const float *kth = nullptr;
+    if (get_kth_values(idx, k, st, &kth)) return 1;
+    idx->st_launches = idx->st_passes = idx->st_reruns = idx->st_candidates = 0;
+    idx->ev_used = 0;
+    idx->st_traverse_ms = 0.0;
+    idx->st_traverse_launches = 0;
+    int64_t launches0 = (int64_t)bb25_launch_count();
+
+    BB25_CUDA(cudaMemsetAsync(ws + o_ctr, 0, 64, st));
+    prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(q_terms, q_off, n_q, term_base, idx->n_vocab, kth,
+                                                                      d_terms, d_nc, d_thr, d_cnt, d_prev, d_err);
+    BB25_LAUNCH_CHECK();
+
+    // tile groups: a small first group makes a loose threshold seed cheap to repair,
+    // later groups run with the exact k-th key of everything seen so far
+    int bounds[4];
+    int ng = 0;
+    const int T = idx->n_tiles;
+    bounds[0] = 0;
+    if (T >= 16) {
+        bounds[1] = std::max(1, T / 16);
+        bounds[2] = std::max(bounds[1] + 1, T / 4);
+        bounds[3] = T;
+        ng = 3;
+    } else {
+        bounds[1] = T;
+        ng = 1;
+    }
+
+    TileArgs ta{};
+    base_args(idx, ta);
+    ta.q_terms = d_terms;
+    ta.q_nocount = d_nc;
+    ta.q_off = q_off;
+    ta.term_base = term_base;
+    ta.thr = d_thr;
+    ta.cand_cnt = d_cnt;
+    ta.cand_key = d_keys;
+    ta.cap = cap;
+    ta.params = *params;
+    ta.work_counter = d_work;
+
+    SelectArgs sa{};
+    sa.cand_cnt = d_cnt;
+    sa.n_prev = d_prev;
+    sa.cand_key = d_keys;
+    sa.thr = d_thr;
+    sa.cap = cap;
+    sa.k = k;
+    sa.n_over = d_nover;
+    sa.doc_len = idx->doc_len;
+    sa.avgdl = idx->avgdl;
+    sa.n_docs = idx->n_docs;
+    sa.doc_id_offset = idx->doc_id_offset;
+    sa.params = *params;
+    sa.out_ids = out_ids;
+    sa.out_scores = out_scores;
+    sa.out_probs = out_probs;
+    sa.n_cand_total = d_ncand;
+
+    const size_t sel_smem = (size_t)cap * 9;
+    BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 9));
+    unsigned int *h_flags = (unsigned int *)idx->pinned;  // [0] n_over, [1] err
+
+    for (int gi = 0; gi < ng; gi++) {
+        int cur_n = (int)n_q;
+        const int32_t *cur_list = nullptr;
+        int flip = 0;
+        for (int iter = 0;; iter++) {
+            if (iter > 200) { set_error("threshold refinement did not converge"); return 1; }
+            ta.q_list = cur_list;
+            ta.n_q = cur_n;
+            ta.tile_begin = bounds[gi];
+            ta.tile_end = bounds[gi + 1];
+            const int pair = idx->ev_used < bb25_index::kMaxEv ? idx->ev_used : -1;
+            if (pair >= 0) {
+                while (idx->n_ev < 2 * (pair + 1)) {
+                    BB25_CUDA(cudaEventCreate(&idx->ev[idx->n_ev]));
+                    idx->n_ev++;
+                }
+                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair], st));
+            }
+            if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) return 1;
+            if (pair >= 0) {
+                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair + 1], st));
+                idx->ev_used++;
+            }
+            idx->st_passes++;
+            BB25_CUDA(cudaMemsetAsync(d_nover, 0, sizeof(unsigned int), st));
+            sa.q_list = cur_list;
+            sa.final_pass = (gi == ng - 1) ? 1 : 0;
+            sa.over_list = d_list[flip];
+            select_kernel<512><<<(unsigned)cur_n, 512, sel_smem, st>>>(sa);
+            BB25_LAUNCH_CHECK();
+            BB25_CUDA(cudaMemcpyAsync(&h_flags[0], d_nover, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            BB25_CUDA(cudaMemcpyAsync(&h_flags[1], d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BB25_CUDA(cudaStreamSynchronize(st));
+            if (h_flags[1]) {
+                set_error("invalid query batch (flags=%u: 1 term id out of range, 2 q_off not monotone)", h_flags[1]);
+                return 1;
+            }
+            const unsigned int n_over = h_flags[0];
+            if (n_over == 0) break;
+            idx->st_reruns += n_over;
+            cur_list = d_list[flip];
+            cur_n = (int)n_over;
+            flip ^= 1;
+        }
+    }
+    unsigned long long h_ncand = 0;
+    BB25_CUDA(cudaMemcpyAsync(idx->pinned, d_ncand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaStreamSynchronize(st));
+    h_ncand = *(unsigned long long *)idx->pinned;
+    idx->st_candidates = (int64_t)h_ncand;
+    for (int i = 0; i < idx->ev_used; i++) {
+        float ms = 0.f;
+        BB25_CUDA(cudaEventElapsedTime(&ms, idx->ev[2 * i], idx->ev[2 * i + 1]));
+        idx->st_traverse_ms += (double)ms;
+    }
+    idx->st_traverse_launches = idx->ev_used;
+    idx->st_launches = (int64_t)bb25_launch_count() - launches0;
+    return 0;
+}
+
+}  // namespace bb25
+
+using namespace bb25;
+
+extern "C" {
+
+int bb25_get_scores(bb25_index *idx, const int32_t *q_terms, int n_terms, float *out_scores, void *stream) {
+    if (!out_scores) { set_error("out_scores is NULL"); return 1; }
+    return run_dense(idx, MODE_SCORES, nullptr, q_terms, n_terms, out_scores, nullptr, 1, (cudaStream_t)stream);
+}
+
+int bb25_get_probabilities(bb25_index *idx, const bb25_params *params, const int32_t *q_terms, int n_terms,
+                           double *out_probs, int64_t out_stride, void *stream) {
+    if (!out_probs || out_stride < 1) { set_error("bad output arguments"); return 1; }
+    if (check_params(params)) return 1;
+    return run_dense(idx, MODE_PROBS, params, q_terms, n_terms, nullptr, out_probs, out_stride, (cudaStream_t)stream);
+}
+
+int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                        const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
+                        float *out_scores, double *out_probs, void *stream) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (check_params(params)) return 1;
+    if (n_queries < 0 || !q_off || !out_ids || !out_probs) { set_error("bad arguments"); return 1; }
+    if (k < 1 || k > kMaxK || (int64_t)k > idx->n_docs) {
+        set_error("k must satisfy 1 <= k <= min(n_docs, %d), got k=%d with n_docs=%lld", kMaxK, k, (long long)idx->n_docs);
+        return 1;
+    }
+    if (n_queries == 0) return 0;
+    if (n_queries > 0x7FFFFFF0ll) { set_error("too many queries in one batch"); return 1; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("cannot select device"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t ends[2];
+    BB25_CUDA(cudaMemcpyAsync(&ends[0], q_off, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaMemcpyAsync(&ends[1], q_off + n_queries, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaStreamSynchronize(st));
+    if (ends[1] < ends[0] || ends[0] < 0) { set_error("bad q_off"); return 1; }
+    if (ends[1] > ends[0] && !q_terms) { set_error("q_terms is NULL"); return 1; }
+    return retrieve_device(idx, params, q_terms, q_off, n_queries, ends[0], ends[1] - ends[0], k, out_ids,
+                           out_scores, out_probs, st);
+}
+
+int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                             const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
+                             float *out_scores, double *out_probs) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (n_queries < 0 || !q_off || !out_ids || !out_probs) { set_error("bad arguments"); return 1; }
+    if (n_queries == 0) return 0;
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("cannot select device"); return 1; }
+    const int64_t nt = q_off[n_queries] - q_off[0];
+    if (nt < 0) { set_error("bad q_off"); return 1; }
+    const size_t nk = (size_t)n_queries * (size_t)(k > 0 ? k : 1);
+    int32_t *d_terms = nullptr;
+    int64_t *d_off = nullptr, *d_ids = nullptr;
+    float *d_sc = nullptr;
+    double *d_pr = nullptr;
+    int rc = 1;
+    cudaStream_t st = nullptr;
+    do {
+        if (cudaMalloc(&d_terms, sizeof(int32_t) * (size_t)(nt > 0 ? nt : 1)) != cudaSuccess) break;
+        if (cudaMalloc(&d_off, sizeof(int64_t) * (size_t)(n_queries + 1)) != cudaSuccess) break;
+        if (cudaMalloc(&d_ids, sizeof(int64_t) * nk) != cudaSuccess) break;
+        if (cudaMalloc(&d_sc, sizeof(float) * nk) != cudaSuccess) break;
+        if (cudaMalloc(&d_pr, sizeof(double) * nk) != cudaSuccess) break;
+        if (nt > 0 && cudaMemcpyAsync(d_terms, q_terms + q_off[0], sizeof(int32_t) * (size_t)nt, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        if (cudaMemcpyAsync(d_off, q_off, sizeof(int64_t) * (size_t)(n_queries + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        // d_terms holds positions [q_off[0], q_off[Q]) -> pass a base-shifted pointer
+        rc = bb25_retrieve_batch(idx, params, d_terms - q_off[0], d_off, n_queries, k, d_ids, d_sc, d_pr, st);
+        if (rc) break;
+        rc = 1;
+        if (cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * nk, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (out_scores && cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * nk, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaMemcpyAsync(out_probs, d_pr, sizeof(double) * nk, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc && bb25_last_error()[0] == 0) set_error("CUDA failure in bb25_retrieve_batch_host: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_terms);
+    cudaFree(d_off);
+    cudaFree(d_ids);
+    cudaFree(d_sc);
+    cudaFree(d_pr);
+    return rc;
+}
+
+int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passes, int64_t *rerun_queries,
+                        int64_t *candidates) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (launches) *launches = idx->st_launches;
+    if (passes) *passes = idx->st_passes;
+    if (rerun_queries) *rerun_queries = idx->st_reruns;
+    if (candidates) *candidates = idx->st_candidates;
+    return 0;
+}
+
+int bb25_retrieve_timing(const bb25_index *idx, double *traverse_ms, int64_t *traverse_launches) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (traverse_ms) *traverse_ms = idx->st_traverse_ms;
+    if (traverse_launches) *traverse_launches = idx->st_traverse_launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""MultiFieldScorer on the B200 path (reference: ``bayesian_bm25/multi_field.py``).
+
+One BayesianBM25Scorer (device index) per field; per-field dense probabilities
+are written column-stacked into one device buffer, fused by the
+log_odds_conjunction kernel and ranked by the dense top-k kernel -- nothing
+leaves the device until the final (k,) result.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .fusion import _resolve_alpha, log_odds_conjunction_device
+from .scorer import BayesianBM25Scorer
+
+MAX_DEVICE_TOPK = 8192
+
+
+class MultiFieldScorer:
+    """Fuses per-field Bayesian probabilities (multi_field.py:24-236)."""
+
+    def __init__(self, fields: list[str], field_weights: dict[str, float] | None = None,
+                 alpha: float | str | None = "auto", base_rate: float | str | None = None,
+                 k1: float = 1.2, b: float = 0.75, method: str = "robertson") -> None:
+        if not fields:
+            raise ValueError("fields must be a non-empty list")
+        if len(fields) != len(set(fields)):
+            raise ValueError("fields must not contain duplicates")
+        self._fields = list(fields)
+        self._alpha = alpha
+        self._base_rate = base_rate
+        self._k1, self._b, self._method = k1, b, method
+        if field_weights is None:
+            self._field_weights = {f: 1.0 / len(fields) for f in fields}
+        else:
+            for f in fields:
+                if f not in field_weights:
+                    raise ValueError(f"field_weights missing key {f!r}")
+            total = sum(field_weights[f] for f in fields)
+            if abs(total - 1.0) > 1e-6:
+                raise ValueError(f"field_weights must sum to 1, got {total}")
+            self._field_weights = {f: field_weights[f] for f in fields}
+        self._scorers: dict[str, BayesianBM25Scorer] = {}
+        self._num_docs = 0
+
+    @property
+    def num_docs(self) -> int:
+        return self._num_docs
+
+    @property
+    def fields(self) -> list[str]:
+        return list(self._fields)
+
+    @property
+    def field_weights(self) -> dict[str, float]:
+        return dict(self._field_weights)
+
+    def _new_scorer(self) -> BayesianBM25Scorer:
+        return BayesianBM25Scorer(k1=self._k1, b=self._b, method=self._method, base_rate=self._base_rate)
+
+    def index(self, documents: list[dict[str, list[str]]], show_progress: bool = True) -> None:
+        """One index per field (multi_field.py:105-139)."""
+        for i, doc in enumerate(documents):
+            for f in self._fields:
+                if f not in doc:
+                    raise ValueError(f"Document {i} missing field {f!r}")
+        self._scorers = {}
+        for f in self._fields:
+            s = self._new_scorer()
+            s.index([doc[f] for doc in documents], show_progress=show_progress)
+            self._scorers[f] = s
+        self._num_docs = len(documents)
+
+    def index_from_csc(self, field_csc: dict[str, dict], pseudo_queries: dict | None = None) -> None:
+        """Extension: adopt prebuilt per-field CSCs (same documents in every field)."""
+        self._scorers = {}
+        for f in self._fields:
+            s = self._new_scorer()
+            s.index_from_csc(field_csc[f], pseudo_queries=(pseudo_queries or {}).get(f))
+            self._scorers[f] = s
+        self._num_docs = self._scorers[self._fields[0]].num_docs
+
+    def add_documents(self, new_documents: list[dict[str, list[str]]], show_progress: bool = True) -> None:
+        if not self._scorers:
+            raise RuntimeError("Call index() before add_documents().")
+        for i, doc in enumerate(new_documents):
+            for f in self._fields:
+                if f not in doc:
+                    raise ValueError(f"New document {i} missing field {f!r}")
+        for f in self._fields:
+            self._scorers[f].add_documents([doc[f] for doc in new_documents], show_progress=show_progress)
+        self._num_docs += len(new_documents)
+
+    def _fused_device(self, per_field_terms) -> torch.Tensor:
+        nf = len(self._fields)
+        first = self._scorers[self._fields[0]]
+        buf = torch.empty((self._num_docs, nf), dtype=torch.float64, device=first._device)
+        for j, f in enumerate(self._fields):
+            # column j of the row-major [N, F] buffer: element d at buf[d, j]
+            self._scorers[f].probabilities_device(per_field_terms[j], out=buf[:, j], stride=nf)
+        w = np.array([self._field_weights[f] for f in self._fields], dtype=np.float64)
+        return log_odds_conjunction_device(buf, alpha=_resolve_alpha(self._alpha, default=0.5), weights=w)
+
+    def get_probabilities(self, query_tokens: list[str]) -> np.ndarray:
+        """Fused probability of every document (multi_field.py:141-174)."""
+        if not self._scorers:
+            raise RuntimeError("Call index() before get_probabilities().")
+        terms = [self._scorers[f]._term_ids(query_tokens) for f in self._fields]
+        return self._fused_device(terms).cpu().numpy()
+
+    def _topk_device(self, fused: torch.Tensor, k: int):
+        k = min(k, fused.numel())
+        if k <= MAX_DEVICE_TOPK:
+            ids = torch.empty(k, dtype=torch.int64, device=fused.device)
+            vals = torch.empty(k, dtype=torch.float64, device=fused.device)
+            _lib.check(_lib.lib().bb25_topk_f64(fused.device.index, fused.data_ptr(), fused.numel(), k,
+                                                ids.data_ptr(), vals.data_ptr(), _lib.stream_ptr()))
+            return ids, vals
+        # very large k: full stable device sort (value desc, id asc)
+        order = torch.sort(fused, descending=True, stable=True).indices[:k]
+        return order, fused[order]
+
+    def retrieve(self, query_tokens: list[str], k: int = 10):
+        """Top-k by fused probability (multi_field.py:176-200); ties resolved by
+        ascending doc id (the reference's argsort leaves them unspecified)."""
+        if not self._scorers:
+            raise RuntimeError("Call index() before get_probabilities().")
+        terms = [self._scorers[f]._term_ids(query_tokens) for f in self._fields]
+        ids, vals = self._topk_device(self._fused_device(terms), k)
+        return ids.cpu().numpy(), vals.cpu().numpy()
+
+    def retrieve_ids(self, per_field_terms, k: int = 10):
+        """Extension: query given as one term-id list per field."""
+        ids, vals = self._topk_device(self._fused_device(per_field_terms), k)
+        return ids.cpu().numpy(), vals.cpu().numpy()

@@ -1,0 +1,380 @@
+"""BayesianBM25Scorer and BlockMaxIndex on the B200 path.
+
+Mirrors the public surface of the reference's ``bayesian_bm25/scorer.py``
+(constructor kwargs, ``index`` / ``retrieve`` / ``get_probabilities`` /
+``add_documents``, properties and error behaviour) with the sparse BM25 engine,
+the tf counting, the posterior and the top-k running as CUDA kernels behind
+libbb25 (include/bb25.h).  Extensions for corpora that do not fit Python lists:
+``index_from_ids`` / ``index_from_csc`` / ``retrieve_ids``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, estimators, index_build
+from .probability import BayesianProbabilityTransform
+
+_VALID_BASE_RATE_METHODS = estimators.VALID_BASE_RATE_METHODS
+MAX_DEVICE_K = 4096      # bb25_retrieve_batch limit; larger k takes the dense path
+QUERY_CHUNK = 16384      # queries per bb25_retrieve_batch call (bounds the workspace)
+
+
+class BlockMaxIndex:
+    """Per-(term, document block) maxima for BMW-style bounds (scorer.py:33-142)."""
+
+    def __init__(self, block_size: int = 128) -> None:
+        if block_size < 1:
+            raise ValueError(f"block_size must be >= 1, got {block_size}")
+        self._block_size = block_size
+        self._block_maxes: np.ndarray | None = None
+        self._n_docs = 0
+        self._n_terms = 0
+
+    def build(self, score_matrix) -> None:
+        """score_matrix: (n_terms, n_docs) per-term BM25 contributions (scorer.py:55-81)."""
+        sm = np.asarray(score_matrix, dtype=np.float64)
+        if sm.ndim != 2:
+            raise ValueError(f"score_matrix must be 2D (n_terms, n_docs), got {sm.ndim}D")
+        self._n_terms, self._n_docs = sm.shape
+        dev = _lib.require_cuda()
+        nb = (self._n_docs + self._block_size - 1) // self._block_size
+        d_sm = torch.from_numpy(np.ascontiguousarray(sm)).to(f"cuda:{dev}")
+        out = torch.empty((self._n_terms, nb), dtype=torch.float64, device=d_sm.device)
+        if self._n_terms and self._n_docs:
+            _lib.check(_lib.lib().bb25_blockmax_dense(dev, d_sm.data_ptr(), self._n_terms, self._n_docs,
+                                                      self._block_size, out.data_ptr(), _lib.stream_ptr()))
+        self._block_maxes = out.cpu().numpy()
+
+    def build_from_scorer(self, scorer: "BayesianBM25Scorer", term_ids) -> None:
+        """Extension: block maxima of `term_ids` straight from the device CSC (an
+        absent posting counts as 0.0; posting values are >= 0), for corpora whose
+        dense (n_terms, n_docs) matrix cannot be materialised."""
+        scorer._require_index("build_from_scorer()")
+        terms = torch.as_tensor(np.asarray(term_ids, dtype=np.int32), device=scorer._device)
+        nb = (scorer.num_docs + self._block_size - 1) // self._block_size
+        out = torch.empty((terms.numel(), nb), dtype=torch.float32, device=scorer._device)
+        _lib.check(_lib.lib().bb25_blockmax_csc(scorer._handle, terms.data_ptr(), terms.numel(),
+                                                self._block_size, out.data_ptr(), _lib.stream_ptr()))
+        self._n_terms, self._n_docs = terms.numel(), scorer.num_docs
+        self._block_maxes = out.cpu().numpy().astype(np.float64)
+
+    def block_upper_bound(self, term_idx: int, block_id: int) -> float:
+        if self._block_maxes is None:
+            raise RuntimeError("Call build() before block_upper_bound().")
+        return float(self._block_maxes[term_idx, block_id])
+
+    def bayesian_block_upper_bound(self, term_idx: int, block_id: int,
+                                   transform: BayesianProbabilityTransform, p_max: float = 0.9) -> float:
+        """transform.wand_upper_bound of the block maximum (scorer.py:101-130)."""
+        return float(transform.wand_upper_bound(self.block_upper_bound(term_idx, block_id), p_max))
+
+    @property
+    def block_size(self) -> int:
+        return self._block_size
+
+    @property
+    def n_blocks(self) -> int:
+        if self._block_maxes is None:
+            raise RuntimeError("Call build() before accessing n_blocks.")
+        return self._block_maxes.shape[1]
+
+
+@dataclass
+class RetrievalResult:
+    """Return type of ``retrieve(explain=True)`` in the reference (scorer.py:145-163)."""
+
+    doc_ids: np.ndarray
+    probabilities: np.ndarray
+    explanations: list | None
+
+
+class BayesianBM25Scorer:
+    """BM25 scorer returning Bayesian-calibrated probabilities (scorer.py:166-640)."""
+
+    def __init__(self, k1: float = 1.2, b: float = 0.75, method: str = "robertson",
+                 alpha: float | None = None, beta: float | None = None,
+                 base_rate: float | str | None = None, base_rate_method: str = "percentile") -> None:
+        if base_rate_method not in _VALID_BASE_RATE_METHODS:
+            raise ValueError(
+                f"base_rate_method must be one of {_VALID_BASE_RATE_METHODS}, got {base_rate_method!r}")
+        if method not in index_build.VALID_METHODS:
+            raise ValueError(f"method must be one of {index_build.VALID_METHODS}, got {method!r}")
+        self._k1, self._b, self._method = k1, b, method
+        self._user_alpha, self._user_beta = alpha, beta
+        self._user_base_rate = base_rate
+        self._base_rate_method = base_rate_method
+        self._transform: BayesianProbabilityTransform | None = None
+        self._doc_lengths: np.ndarray | None = None
+        self._avgdl: float | None = None
+        self._corpus_tokens: list[list[str]] | None = None
+        self._vocab: dict[str, int] = {}
+        self._handle = None
+        self._device = None
+        self._num_docs = 0
+        self._n_vocab = 0
+        self._doc_id_offset = 0
+
+    def __del__(self):
+        self._release()
+
+    def _release(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                _lib.lib().bb25_index_destroy(h)
+            except Exception:
+                pass
+
+    # ---- properties (scorer.py:224-248) ------------------------------------------
+    @property
+    def num_docs(self) -> int:
+        return int(self._num_docs)
+
+    @property
+    def doc_lengths(self) -> np.ndarray:
+        if self._doc_lengths is None:
+            raise RuntimeError("Call index() before accessing doc_lengths.")
+        return self._doc_lengths
+
+    @property
+    def avgdl(self) -> float:
+        if self._avgdl is None:
+            raise RuntimeError("Call index() before accessing avgdl.")
+        return self._avgdl
+
+    @property
+    def base_rate(self) -> float | None:
+        return None if self._transform is None else self._transform.base_rate
+
+    @property
+    def transform(self) -> BayesianProbabilityTransform | None:
+        return self._transform
+
+    def _require_index(self, what: str) -> None:
+        if self._transform is None or self._handle is None:
+            raise RuntimeError(f"Call index() before {what}.")
+
+    # ---- indexing -------------------------------------------------------------------
+    def index(self, corpus_tokens: list[list[str]], show_progress: bool = True) -> None:
+        """Build the index from tokenised documents (scorer.py:250-285)."""
+        vocab: dict[str, int] = {}
+        flat: list[int] = []
+        offs = np.zeros(len(corpus_tokens) + 1, dtype=np.int64)
+        for i, doc in enumerate(corpus_tokens):
+            for tok in doc:
+                j = vocab.get(tok)
+                if j is None:
+                    j = vocab[tok] = len(vocab)
+                flat.append(j)
+            offs[i + 1] = len(flat)
+        if "" not in vocab:  # bm25s reserves an id for the empty token
+            vocab[""] = len(vocab)
+        self._corpus_tokens = corpus_tokens
+        self._vocab = vocab
+        self.index_from_ids(np.asarray(flat, dtype=np.int32), offs, len(vocab))
+
+    def index_from_ids(self, token_ids, doc_offsets, n_vocab: int) -> None:
+        """Extension: index a corpus given as a flat token-id array plus document
+        offsets (no Python lists / per-document sets)."""
+        dev = _lib.require_cuda()
+        device = torch.device(f"cuda:{dev}")
+        t = torch.as_tensor(np.asarray(token_ids), device=device)
+        o = torch.as_tensor(np.asarray(doc_offsets, dtype=np.int64), device=device)
+        if o.numel() < 2:
+            raise ValueError("cannot index an empty corpus")
+        csc = index_build.build_csc(t, o, int(n_vocab), self._k1, self._b, self._method)
+        offs = np.asarray(doc_offsets, dtype=np.int64)
+        tok = np.asarray(token_ids)
+        sample = [tok[offs[i]:offs[i + 1]][:5] for i in self._pseudo_query_docs(len(offs) - 1)]
+        self.index_from_csc(csc, pseudo_queries=sample)
+
+    def index_from_csc(self, csc: dict, pseudo_queries=None) -> None:
+        """Extension: adopt a prebuilt CSC (dict of tensors as produced by
+        index_build / synthetic) and estimate alpha / beta / base rate from
+        `pseudo_queries` (lists of term ids; default: none -> user values or 1, 0)."""
+        dev = _lib.require_cuda()
+        device = torch.device(f"cuda:{dev}")
+        self._release()
+        data = csc["data"].to(device, torch.float32).contiguous()
+        indices = csc["indices"].to(device, torch.int32).contiguous()
+        indptr = csc["indptr"].to(device, torch.int64).contiguous()
+        doc_len = csc["doc_len"].to(device, torch.int32).contiguous()
+        n_docs = int(csc["num_docs"])
+        n_vocab = indptr.numel() - 1
+        if not (csc["avgdl"] > 0):
+            raise ValueError("corpus has no tokens")
+        handle = C.c_void_p()
+        _lib.check(_lib.lib().bb25_index_create(
+            dev, n_docs, n_vocab, data.numel(), data.data_ptr(), indices.data_ptr(), indptr.data_ptr(),
+            doc_len.data_ptr(), float(csc["avgdl"]), int(csc.get("doc_id_offset", 0)), C.byref(handle)))
+        self._handle, self._device = handle, device
+        self._num_docs, self._n_vocab = n_docs, n_vocab
+        self._doc_id_offset = int(csc.get("doc_id_offset", 0))
+        self._doc_lengths = doc_len.cpu().numpy().astype(np.float64)
+        self._avgdl = float(csc["avgdl"])
+        self._df = (indptr[1:] - indptr[:-1]).cpu().numpy()
+
+        per_query = []
+        for q in (pseudo_queries or []):
+            if len(q) == 0:
+                continue
+            s = self._scores_device(np.asarray(q, dtype=np.int32))
+            nz = s[s > 0]
+            if nz.numel() > 0:
+                per_query.append(nz.cpu().numpy())
+        alpha, beta = estimators.sigmoid_parameters(per_query, self._user_alpha, self._user_beta)
+        base_rate = None
+        if self._user_base_rate == "auto":
+            base_rate = estimators.estimate_base_rate(per_query, n_docs, self._base_rate_method)
+        elif isinstance(self._user_base_rate, (int, float)):
+            base_rate = float(self._user_base_rate)
+        self._transform = BayesianProbabilityTransform(alpha=alpha, beta=beta, base_rate=base_rate)
+
+    @staticmethod
+    def _pseudo_query_docs(n: int) -> np.ndarray:
+        """Documents whose first five tokens serve as pseudo-queries (scorer.py:295-298)."""
+        return np.random.default_rng(42).choice(n, size=min(n, 50), replace=False)
+
+    def add_documents(self, new_corpus_tokens: list[list[str]], show_progress: bool = True) -> None:
+        """Append documents and rebuild (scorer.py:469-492)."""
+        if self._corpus_tokens is None:
+            raise RuntimeError("Call index() before add_documents().")
+        self.index(self._corpus_tokens + new_corpus_tokens, show_progress=show_progress)
+
+    # ---- query side ------------------------------------------------------------------
+    def _term_ids(self, tokens) -> np.ndarray:
+        v = self._vocab
+        return np.asarray([v[t] for t in tokens if t in v], dtype=np.int32)
+
+    def _params(self) -> _lib.Params:
+        t = self._transform
+        return _lib.make_params(t.alpha, t.beta, t.base_rate, prior_free=t._training_mode == "prior_free")
+
+    def _scores_device(self, term_ids: np.ndarray) -> torch.Tensor:
+        out = torch.empty(self._num_docs, dtype=torch.float32, device=self._device)
+        q = np.ascontiguousarray(term_ids, dtype=np.int32)
+        _lib.check(_lib.lib().bb25_get_scores(self._handle, q.ctypes.data, q.size, out.data_ptr(),
+                                              _lib.stream_ptr()))
+        return out
+
+    def get_scores_ids(self, term_ids) -> np.ndarray:
+        """fp32 BM25 scores of all documents for in-vocabulary term ids (what
+        ``self._bm25.get_scores`` is for the reference, scorer.py:306,583)."""
+        self._require_index("get_scores_ids()")
+        return self._scores_device(np.asarray(term_ids, dtype=np.int32)).cpu().numpy()
+
+    def probabilities_device(self, term_ids, out: torch.Tensor | None = None, stride: int = 1) -> torch.Tensor:
+        """Dense fp64 probabilities on the device; `out` may be a column of a wider
+        buffer (element d written at out.data_ptr() + d*stride)."""
+        self._require_index("get_probabilities()")
+        q = np.ascontiguousarray(term_ids, dtype=np.int32)
+        if out is None:
+            out = torch.empty(self._num_docs, dtype=torch.float64, device=self._device)
+            stride = 1
+        p = self._params()
+        _lib.check(_lib.lib().bb25_get_probabilities(self._handle, C.byref(p), q.ctypes.data, q.size,
+                                                     out.data_ptr(), stride, _lib.stream_ptr()))
+        return out
+
+    def get_probabilities(self, query_tokens: list[str]) -> np.ndarray:
+        """Probabilities for ALL documents, 0.0 where the score is <= 0 (scorer.py:564-590)."""
+        if self._transform is None:
+            raise RuntimeError("Call index() before get_probabilities().")
+        return self.probabilities_device(self._term_ids(query_tokens)).cpu().numpy()
+
+    def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
+        """Device-resident batch retrieve: q_terms int32 [total], q_off int64 [Q+1]
+        CUDA tensors -> (ids int64 [Q,k], scores fp32 [Q,k], probs fp64 [Q,k]) CUDA tensors."""
+        self._require_index("retrieve()")
+        nq = q_off.numel() - 1
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self._device)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=self._device)
+        pr = torch.empty((nq, k), dtype=torch.float64, device=self._device)
+        p = self._params()
+        for s in range(0, nq, QUERY_CHUNK):
+            e = min(nq, s + QUERY_CHUNK)
+            _lib.check(_lib.lib().bb25_retrieve_batch(
+                self._handle, C.byref(p), q_terms.data_ptr(), q_off[s:].data_ptr(), e - s, k,
+                ids[s:].data_ptr(), sc[s:].data_ptr(), pr[s:].data_ptr(), _lib.stream_ptr()))
+        return ids, sc, pr
+
+    def retrieve_ids(self, q_terms, q_off, k: int = 10, return_scores: bool = False):
+        """Extension: batch retrieve for queries given as in-vocabulary term ids
+        (flat int32 array + int64 offsets), host in / host out."""
+        self._require_index("retrieve()")
+        if k > self._num_docs:
+            raise ValueError(
+                f"k of {k} is larger than the number of available scores, which is {self._num_docs}")
+        q_terms = np.ascontiguousarray(q_terms, dtype=np.int32)
+        q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        if k > MAX_DEVICE_K:
+            return self._retrieve_large_k(q_terms, q_off, k, return_scores)
+        # inputs go up from pinned staging, results come back into pinned buffers
+        # (torch's caching host allocator recycles them), one sync at the end
+        if q_terms.size:
+            hp = torch.empty(q_terms.size, dtype=torch.int32, pin_memory=True)
+            hp.numpy()[:] = q_terms
+            dt = hp.to(self._device, non_blocking=True)
+        else:
+            dt = torch.zeros(1, dtype=torch.int32, device=self._device)
+        ho = torch.empty(q_off.size, dtype=torch.int64, pin_memory=True)
+        ho.numpy()[:] = q_off
+        do = ho.to(self._device, non_blocking=True)
+        ids, sc, pr = self.retrieve_ids_device(dt, do, k)
+        outs = [ids, sc, pr] if return_scores else [ids, pr]
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+        for h, t in zip(host, outs):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return tuple(h.numpy() for h in host)
+
+    def _retrieve_large_k(self, q_terms, q_off, k, return_scores):
+        """k beyond the fused kernel's limit: dense scores and probabilities from the
+        traversal kernel, then a full device sort of (score desc, id asc) keys."""
+        nq = len(q_off) - 1
+        ids = np.empty((nq, k), dtype=np.int64)
+        sc = np.empty((nq, k), dtype=np.float32)
+        pr = np.empty((nq, k), dtype=np.float64)
+        inv = (2 ** 31 - 1) - torch.arange(self._num_docs, device=self._device, dtype=torch.int64)
+        for i in range(nq):
+            t = q_terms[q_off[i]:q_off[i + 1]]
+            s = self._scores_device(t)
+            p = self.probabilities_device(t)
+            key = (s.view(torch.int32).to(torch.int64) << 31) | inv
+            top = torch.sort(key, descending=True).indices[:k]
+            ids[i] = (top + self._doc_id_offset).cpu().numpy()
+            sc[i] = s[top].cpu().numpy()
+            pr[i] = p[top].cpu().numpy()
+        return (ids, sc, pr) if return_scores else (ids, pr)
+
+    def retrieve(self, query_tokens: list[list[str]], k: int = 10, show_progress: bool = False,
+                 explain: bool = False):
+        """Top-k documents per query with Bayesian probabilities (scorer.py:494-562).
+        Ranking is by fp32 BM25 score (ties: ascending doc id); probabilities are
+        attached in rank order.  Returns (doc_ids [Q,k] int64, probabilities [Q,k] float64)."""
+        if self._transform is None:
+            raise RuntimeError("Call index() before retrieve().")
+        if explain:
+            raise NotImplementedError(
+                "explain=True builds FusionDebugger traces (bayesian_bm25/debug.py), which is outside "
+                "the B200 hot path; run the reference's debugger on the returned ids")
+        per_q = [self._term_ids(q) for q in query_tokens]
+        off = np.zeros(len(per_q) + 1, dtype=np.int64)
+        if per_q:
+            np.cumsum([len(q) for q in per_q], out=off[1:])
+        flat = np.concatenate(per_q).astype(np.int32) if per_q and off[-1] > 0 else np.zeros(0, dtype=np.int32)
+        return self.retrieve_ids(flat, off, k)
+
+    def stats(self) -> dict:
+        """Counters of the last batch retrieve (launches, traversal passes, re-runs)."""
+        vals = [C.c_int64() for _ in range(4)]
+        _lib.check(_lib.lib().bb25_retrieve_stats(self._handle, *[C.byref(v) for v in vals]))
+        out = dict(zip(("launches", "passes", "rerun_queries", "candidates"), (v.value for v in vals)))
+        ms, nl = C.c_double(), C.c_int64()
+        _lib.check(_lib.lib().bb25_retrieve_timing(self._handle, C.byref(ms), C.byref(nl)))
+        out["traverse_ms"], out["traverse_launches"] = ms.value, nl.value
+        return out

@@ -1,0 +1,63 @@
+"""Document-range sharding across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).
+Rank s holds the CSC rows of documents [s*N/S, (s+1)*N/S) with local doc ids and a
+``doc_id_offset``; posting values carry the GLOBAL idf / length statistics, so a
+shard's fp32 scores equal the unsharded index's.  A query batch is scored by
+every rank on its shard (no data-path collective), then ONE exchange step
+all-gathers the per-shard [Q,k] (id, score, probability) lists and every rank
+merges them on its device with the same (score desc, id asc) order.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .index_build import shard_bounds, shard_csc
+
+
+def local_shard(csc: dict, rank: int, world_size: int) -> dict:
+    lo, hi = shard_bounds(int(csc["num_docs"]), world_size)[rank]
+    return shard_csc(csc, lo, hi)
+
+
+def allgather_topk(ids: torch.Tensor, scores: torch.Tensor, probs: torch.Tensor, group=None):
+    """[Q,k] x3 per rank -> [S,Q,k] x3 on every rank (works on NCCL and gloo)."""
+    world = dist.get_world_size(group)
+    outs = []
+    for t in (ids, scores, probs):
+        t = t.contiguous()
+        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t, group=group)
+        outs.append(buf.view((world,) + tuple(t.shape)))
+    return tuple(outs)
+
+
+def merge_topk_device(ids: torch.Tensor, scores: torch.Tensor, probs: torch.Tensor):
+    """[S,Q,k] x3 CUDA tensors -> merged [Q,k] x3 (libbb25 merge kernel)."""
+    s, q, k = ids.shape
+    out_ids = torch.empty((q, k), dtype=torch.int64, device=ids.device)
+    out_sc = torch.empty((q, k), dtype=torch.float32, device=ids.device)
+    out_pr = torch.empty((q, k), dtype=torch.float64, device=ids.device)
+    _lib.check(_lib.lib().bb25_merge_topk(
+        ids.device.index, ids.contiguous().data_ptr(), scores.contiguous().data_ptr(),
+        probs.contiguous().data_ptr(), s, q, k, out_ids.data_ptr(), out_sc.data_ptr(), out_pr.data_ptr(),
+        _lib.stream_ptr()))
+    return out_ids, out_sc, out_pr
+
+
+class ShardedRetriever:
+    """Wraps a rank-local BayesianBM25Scorer (indexed on this rank's shard)."""
+
+    def __init__(self, scorer, group=None):
+        self.scorer = scorer
+        self.group = group
+
+    def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
+        ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
+            return merge_topk_device(g_ids, g_sc, g_pr)
+        return ids, sc, pr

@@ -1,0 +1,190 @@
+/*
+ * bb25.h -- C ABI of libbb25.so, the B200 (sm_100a) implementation of the
+ * Bayesian-BM25 query-time hot path.
+ *
+ * The reference (cognica-io/bayesian-bm25 v0.12.1) is pure Python + NumPy and has
+ * no FFI of its own; its seam for this path is the five calls it makes into the
+ * third-party `bm25s` package plus plain NumPy functions.  Each entry point
+ * below names the reference interface (file:line, relative to the upstream
+ * tree) it replaces.  INTEGRATION.md shows the ctypes binding a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure;
+ *    bb25_last_error() returns a thread-local message for the last failure.
+ *  - "dev" pointers are CUDA device pointers on the index's device, "host"
+ *    pointers are ordinary host memory, "any" may be either (resolved through
+ *    unified addressing).  All buffers are caller-owned.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - There is no CPU fallback: without a usable CUDA device every compute call
+ *    fails with an error.
+ *  - An index handle is immutable after creation; query calls on ONE handle
+ *    are serialised internally (they share a device workspace).
+ *  - Doc ids are int64 in the interface; one index (= one shard) holds at most
+ *    2^29 documents.  Scores are fp32, probabilities fp64, as in the reference.
+ */
+#ifndef BB25_H
+#define BB25_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB25_VERSION 100
+
+typedef struct bb25_index bb25_index;
+
+/* BayesianProbabilityTransform state used at inference time
+ * (bayesian_bm25/probability.py:71-94). */
+typedef struct bb25_params {
+    double alpha;      /* sigmoid steepness   (probability.py:82) */
+    double beta;       /* sigmoid midpoint    (probability.py:83) */
+    int has_base_rate; /* base_rate is not None (probability.py:84) */
+    double base_rate;
+    int prior_mode;    /* 0 composite prior (probability.py:201),
+                          1 prior_free -> 0.5  (probability.py:192-193) */
+} bb25_params;
+
+/* gating names of fusion.py:156-169 */
+enum { BB25_GATE_NONE = 0, BB25_GATE_RELU = 1, BB25_GATE_SWISH = 2, BB25_GATE_GELU = 3, BB25_GATE_SOFTPLUS = 4 };
+
+const char *bb25_last_error(void);
+int bb25_version(void);
+/* number of CUDA kernels this library has launched since it was loaded */
+unsigned long long bb25_launch_count(void);
+/* number of CUDA devices visible (0 when there is none / no driver) */
+int bb25_device_count(void);
+
+/* ---- index ------------------------------------------------------------- */
+
+/*
+ * Upload one shard of a bm25s-style CSC score matrix: replaces the state
+ * bm25s.BM25.index() leaves behind for the reference (scorer.py:262, read back
+ * through .scores at scorer.py:227) together with the reference's own
+ * doc_lengths / avgdl (scorer.py:264-267).
+ *   data[nnz]      fp32 posting values (idf*tfc)                      (any)
+ *   indices[nnz]   int32 LOCAL doc ids, ascending inside a column      (any)
+ *   indptr[V+1]    int64 column starts                                 (any)
+ *   doc_len[N]     int32 token counts of the shard's documents         (any)
+ *   avgdl          GLOBAL mean document length
+ *   doc_id_offset  added to local ids in every returned id (sharding)
+ * Builds the per-(term, doc-tile) skip table used by the traversal kernel.
+ */
+int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz,
+                      const float *data, const int32_t *indices, const int64_t *indptr,
+                      const int32_t *doc_len, double avgdl, int64_t doc_id_offset,
+                      bb25_index **out);
+void bb25_index_destroy(bb25_index *idx);
+int bb25_index_info(const bb25_index *idx, int64_t *n_docs, int64_t *n_vocab, int64_t *nnz,
+                    int *tile_docs, int *n_tiles, int64_t *device_bytes);
+
+/* ---- a1/a4: dense per-query outputs -------------------------------------- */
+
+/* bm25s BM25.get_scores as called at scorer.py:306 and :583: fp32 [N], adds in
+ * query-term order, duplicates included.  q_terms: host, in-vocabulary ids. */
+int bb25_get_scores(bb25_index *idx, const int32_t *q_terms, int n_terms,
+                    float *out_scores /*dev [N]*/, void *stream);
+
+/* BayesianBM25Scorer.get_probabilities (scorer.py:564-590): fp64, exactly 0.0
+ * where the score is <= 0.  Element d is written at out_probs[d*out_stride]
+ * (out_stride >= 1) so several fields can be column-stacked as
+ * multi_field.py:158-161 does. */
+int bb25_get_probabilities(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                           int n_terms, double *out_probs /*dev*/, int64_t out_stride,
+                           void *stream);
+
+/* ---- a2/a3/a5/a6: batched top-k retrieval ------------------------------- */
+
+/*
+ * BayesianBM25Scorer.retrieve (scorer.py:494-536) for a batch of queries:
+ * bm25s retrieve (scores + top-k by fp32 score, scorer.py:525-529) followed by
+ * _scores_to_probabilities (scorer.py:603-640) with tf = number of distinct
+ * query terms matched (scorer.py:592-601).  Rank order is (score desc, doc id
+ * asc); when fewer than k documents match, the lowest-id zero-score documents
+ * fill the tail with probability 0.0.
+ *   q_terms[q_off[Q]]  int32 in-vocabulary term ids, query order, duplicates kept (dev)
+ *   q_off[Q+1]         int64 offsets                                            (dev)
+ *   out_ids[Q*k] int64, out_scores[Q*k] fp32 (may be NULL), out_probs[Q*k] fp64 (dev)
+ * Requires 1 <= k <= min(n_docs, 4096).  Synchronises `stream` before returning.
+ */
+int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                        const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
+                        float *out_scores, double *out_probs, void *stream);
+
+/* Same call with HOST buffers: copies the queries in, runs the batch, copies
+ * the results out (the end-to-end path the Python wrapper uses). */
+int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                             const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
+                             float *out_scores, double *out_probs);
+
+/* statistics of the last bb25_retrieve_batch on this handle: kernel launches,
+ * traversal passes (1 per tile group + re-runs), re-run (query,group) units,
+ * candidates emitted. */
+int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passes,
+                        int64_t *rerun_queries, int64_t *candidates);
+
+/* Device time of the traversal kernel in the last bb25_retrieve_batch on this handle,
+ * measured with CUDA events on the call's stream around every traversal launch
+ * (sum over launches, and their number).  Used for the roofline figure. */
+int bb25_retrieve_timing(const bb25_index *idx, double *traverse_ms, int64_t *traverse_launches);
+
+/* K7 (no reference counterpart): merge S per-shard [Q,k] lists (global ids,
+ * each sorted by (score desc, id asc)) into the global [Q,k].  All dev. */
+int bb25_merge_topk(int device, const int64_t *ids, const float *scores, const double *probs,
+                    int n_shards, int64_t n_queries, int k, int64_t *out_ids, float *out_scores,
+                    double *out_probs, void *stream);
+
+/* top-k of a dense fp64 vector (values >= 0), (value desc, index asc):
+ * MultiFieldScorer.retrieve's argsort (multi_field.py:199) made deterministic. */
+int bb25_topk_f64(int device, const double *vals /*dev [n]*/, int64_t n, int k,
+                  int64_t *out_ids /*dev [k]*/, double *out_vals /*dev [k]*/, void *stream);
+
+/* ---- a7-a11: BayesianProbabilityTransform, elementwise, all dev fp64 ------ */
+
+int bb25_sigmoid(int device, const double *x, int64_t n, double *out, void *stream);              /* probability.py:29-41 */
+int bb25_logit(int device, const double *p, int64_t n, double *out, void *stream);                /* probability.py:44-48 */
+int bb25_likelihood(int device, const bb25_params *p, const double *score, int64_t n, double *out, void *stream); /* :106-108 */
+int bb25_tf_prior(int device, const double *tf, int64_t n, double *out, void *stream);            /* :110-115 */
+int bb25_norm_prior(int device, const double *ratio, int64_t n, double *out, void *stream);       /* :117-129 */
+int bb25_composite_prior(int device, const double *tf, const double *ratio, int64_t n, double *out, void *stream); /* :131-140 */
+int bb25_posterior(int device, const double *lik, const double *prior, int has_base_rate,
+                   double base_rate, int64_t n, double *out, void *stream);                       /* :142-169 */
+/* score_to_probability (:171-203).  prior == NULL: params->prior_mode decides;
+ * prior != NULL: explicit per-element prior (the prior_fn branch :194-199,
+ * evaluated by the caller), clamped to [1e-10, 1-1e-10]. */
+int bb25_score_to_probability(int device, const bb25_params *p, const double *score,
+                              const double *tf, const double *ratio, const double *prior,
+                              int64_t n, double *out, void *stream);
+int bb25_wand_upper_bound(int device, const bb25_params *p, const double *bm25_ub, double p_max,
+                          int64_t n, double *out, void *stream);                                  /* :205-236 */
+
+/* ---- a13/a14: fusion ------------------------------------------------------- */
+
+/* cosine_to_probability (fusion.py:25-45); element i written at out[i*out_stride] */
+int bb25_cosine_to_probability(int device, const double *cos, int64_t n, double *out,
+                               int64_t out_stride, void *stream);
+/* log_odds_conjunction (fusion.py:172-280) over rows of probs[m][n].
+ * weights: dev [n] or NULL (unweighted mean branch).  scale = n ** alpha with
+ * alpha already resolved by the caller (fusion.py:106-116,260,270).
+ * Weight validation (fusion.py:253-258) is the caller's. */
+int bb25_log_odds_conjunction(int device, const double *probs, int64_t m, int n,
+                              const double *weights, double scale, int gating,
+                              double gating_beta, int has_max_logit, double max_logit,
+                              double *out, void *stream);
+
+/* ---- a12: BlockMaxIndex ---------------------------------------------------- */
+
+/* BlockMaxIndex.build (scorer.py:55-81) on a dense [n_terms][n_docs] fp64
+ * matrix -> [n_terms][ceil(n_docs/block_size)] fp64.  All dev. */
+int bb25_blockmax_dense(int device, const double *score_matrix, int64_t n_terms, int64_t n_docs,
+                        int block_size, double *out, void *stream);
+/* The same table for `n_terms` columns of the index (absent posting = 0.0). */
+int bb25_blockmax_csc(bb25_index *idx, const int32_t *terms /*dev*/, int n_terms, int block_size,
+                      float *out /*dev [n_terms][n_blocks]*/, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BB25_H */

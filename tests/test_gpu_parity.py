@@ -1,0 +1,424 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+committed golden vectors.  Bars (BASELINE.json north_star): top-k ids bit-exact with
+ties by doc id, fp32 scores bit-exact (<= 1e-5 rel allowed), probabilities within
+1e-6 absolute -- asserted here at PROB_TOL = 1e-9."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-9
+
+from bb25_testutil import case_scores  # noqa: E402
+
+
+def _pkg():
+    import bayesian_bm25_b200 as pkg
+    return pkg
+
+
+def _host(csc):
+    return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in csc.items()}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+
+
+# ---------------------------------------------------------------------------------
+# elementwise probability / fusion surfaces vs vectors produced by the reference
+# ---------------------------------------------------------------------------------
+def test_probability_transform_vs_reference(golden_pf):
+    pkg, g = _pkg(), golden_pf
+    T = pkg.BayesianProbabilityTransform
+    s, tf, r = g["sweep_score"], g["sweep_tf"], g["sweep_ratio"]
+    for i, (a, b, br) in enumerate(g["sweep_params"]):
+        t = T(a, b, base_rate=None if br < 0 else float(br))
+        np.testing.assert_allclose(t.score_to_probability(s, tf, r), g[f"sweep_prob_{i}"], rtol=0, atol=PROB_TOL)
+        np.testing.assert_allclose(t.wand_upper_bound(s.astype(np.float64)), g[f"sweep_wand_{i}"], rtol=0, atol=PROB_TOL)
+        np.testing.assert_allclose(t.likelihood(s), g[f"sweep_like_{i}"], rtol=0, atol=PROB_TOL)
+        t._training_mode = "prior_free"
+        np.testing.assert_allclose(t.score_to_probability(s, tf, r), g[f"sweep_priorfree_{i}"], rtol=0, atol=PROB_TOL)
+    np.testing.assert_allclose(T.tf_prior(tf), g["sweep_tf_prior"], atol=1e-15)
+    np.testing.assert_allclose(T.norm_prior(r), g["sweep_norm_prior"], atol=1e-15)
+    np.testing.assert_allclose(T.composite_prior(tf, r), g["sweep_composite"], atol=1e-15)
+    np.testing.assert_allclose(T.posterior(g["post_l"], g["post_p"]), g["post_nobr"], atol=1e-15)
+    np.testing.assert_allclose(T.posterior(g["post_l"], g["post_p"], base_rate=0.02), g["post_br"], atol=1e-15)
+    np.testing.assert_allclose(pkg.sigmoid(g["sig_x"]), g["sig_y"], atol=1e-15)
+    np.testing.assert_allclose(pkg.logit(g["logit_p"]), g["logit_y"], atol=1e-12)
+    np.testing.assert_allclose(pkg.cosine_to_probability(g["cos_x"]), g["cos_y"], atol=0)
+    # SURVEY 8c known answers + scalar-in/float-out convention (tests/test_wand.py:109-120)
+    t = T(1.5, 1.0, base_rate=0.01)
+    np.testing.assert_allclose(t.score_to_probability(np.array([.5, 1, 1.5, 2, 3]), np.array([1, 2, 3, 5, 8.]),
+                                                      np.array([.3, .5, .8, 1, 1.5])), g["g1"], atol=PROB_TOL)
+    assert isinstance(t.wand_upper_bound(5.0), float)
+    assert isinstance(t.score_to_probability(1.0, 2.0, 0.5), float)
+    assert T(1.5, 2.0, .01).wand_upper_bound(5.0) == pytest.approx(0.8911075788989186, abs=PROB_TOL)
+    assert T.posterior(0.7, 0.5, base_rate=0.01) == pytest.approx(0.02302631578947368, abs=1e-15)
+    assert T.tf_prior(0) == pytest.approx(0.2) and T.tf_prior(10) == pytest.approx(0.9)
+    assert T.norm_prior(0.5) == pytest.approx(0.9) and T.norm_prior(1.0) == pytest.approx(0.3)
+    # custom prior_fn runs on the host, Bayes update on the device
+    tp = T(1.0, 0.0, prior_fn=lambda s_, tf_, r_: np.full(np.shape(s_), 0.5))
+    np.testing.assert_allclose(tp.score_to_probability(s, tf, r), T(1.0, 0.0).likelihood(s), atol=PROB_TOL)
+
+
+@pytest.mark.parametrize("nsig", [1, 2, 3, 5, 9])
+def test_log_odds_conjunction_vs_reference(golden_pf, nsig):
+    pkg, g = _pkg(), golden_pf
+    loc = pkg.log_odds_conjunction
+    P, w = g[f"loc_in_{nsig}"], g[f"loc_w_{nsig}"]
+    chk = lambda got, key: np.testing.assert_allclose(got, g[key], rtol=0, atol=PROB_TOL)
+    chk(loc(P), f"loc_unw_{nsig}")
+    chk(loc(P, alpha=0.0), f"loc_unw_a0_{nsig}")
+    chk(loc(P, alpha="auto"), f"loc_unw_auto_{nsig}")
+    chk(loc(P, weights=w), f"loc_w_{nsig}_none")
+    chk(loc(P, alpha=0.5, weights=w), f"loc_w_{nsig}_a05")
+    for gt in ("relu", "swish", "gelu", "softplus"):
+        chk(loc(P, alpha=0.5, weights=w, gating=gt), f"loc_{gt}_{nsig}")
+        chk(loc(P, gating=gt, gating_beta=2.0), f"loc_{gt}_b2_{nsig}")
+    chk(loc(P, weights=w, max_logit=3.0), f"loc_clip_{nsig}")
+    if nsig == 3:
+        assert loc(np.array([.85, .7, .6])) == pytest.approx(0.8487403513785625, abs=PROB_TOL)
+        with pytest.raises(ValueError, match="non-negative"):
+            loc(P, weights=[-0.1, 0.6, 0.5])
+        with pytest.raises(ValueError, match="sum to 1"):
+            loc(P, weights=[0.3, 0.3, 0.3])
+        with pytest.raises(ValueError, match="gating"):
+            loc(P, gating="tanh")
+    if nsig == 2:
+        np.testing.assert_allclose(loc(g["g8_in"], weights=[.6, .4]), g["g8a"], atol=PROB_TOL)
+        np.testing.assert_allclose(loc(g["g8_in"], alpha=.5, weights=[.6, .4]), g["g8b"], atol=PROB_TOL)
+        # BM25-inactive document in a fusion
+        assert loc(np.array([0.0, 0.0]), alpha=.5, weights=[.5, .5]) == pytest.approx(7.208823232633578e-15, rel=1e-9)
+
+
+# ---------------------------------------------------------------------------------
+# scorer vs outputs of the reference's scorer.py (string API, full index() path)
+# ---------------------------------------------------------------------------------
+def test_scorer_cases_vs_reference(golden_scorer):
+    pkg = _pkg()
+    arrays, metas = golden_scorer
+    for m in metas:
+        p = m["prefix"]
+        sc = pkg.BayesianBM25Scorer(k1=m["k1"], b=m["b"], method=m["method"], base_rate=m["base_rate_arg"],
+                                    base_rate_method=m["base_rate_method"])
+        sc.index(m["corpus"], show_progress=False)
+        assert sc.num_docs == m["num_docs"]
+        assert sc.avgdl == m["avgdl"]
+        np.testing.assert_array_equal(sc.doc_lengths, arrays[p + "doc_len"])
+        assert sc.transform.alpha == m["alpha"], m["name"]
+        assert sc.transform.beta == m["beta"], m["name"]
+        if m["base_rate"] is None:
+            assert sc.base_rate is None
+        else:
+            assert sc.base_rate == pytest.approx(m["base_rate"], rel=1e-12)
+        for k in m["ks"]:
+            if f"{p}ids_k{k}" not in arrays:
+                with pytest.raises(ValueError):
+                    sc.retrieve(m["queries"], k=k)
+                continue
+            ids, probs = sc.retrieve(m["queries"], k=k)
+            assert ids.shape == probs.shape == (len(m["queries"]), k)
+            np.testing.assert_array_equal(ids, arrays[f"{p}ids_k{k}"], err_msg=f"{m['name']} k={k}")
+            np.testing.assert_allclose(probs, arrays[f"{p}probs_k{k}"], rtol=0, atol=PROB_TOL)
+        for i in range(m["n_dense"]):
+            dense = sc.get_probabilities(m["queries"][i])
+            np.testing.assert_allclose(dense, arrays[p + "dense_probs"][i], rtol=0, atol=PROB_TOL)
+            assert np.array_equal(dense == 0.0, arrays[p + "dense_probs"][i] == 0.0)  # exact zeros
+            qt = arrays[p + "q_terms"][arrays[p + "q_off"][i]:arrays[p + "q_off"][i + 1]]
+            np.testing.assert_array_equal(sc.get_scores_ids(sc._term_ids(m["queries"][i])),
+                                          arrays[p + "dense_scores"][i])
+            assert len(qt) == len(sc._term_ids(m["queries"][i]))
+
+
+def test_config1_vs_reference(golden_config1):
+    """BASELINE configs[0]: the reference's scalability corpus, 10k docs, 100 queries, k=10."""
+    pkg = _pkg()
+    from bayesian_bm25_b200 import synthetic
+    arrays, meta = golden_config1
+    corpus, queries = synthetic.scalability_corpus(10_000, 10_000, 100, np.random.default_rng(42))
+    sc = pkg.BayesianBM25Scorer(k1=1.2, b=0.75, method="lucene", base_rate="auto")
+    sc.index(corpus, show_progress=False)
+    assert sc.transform.alpha == meta["alpha"] and sc.transform.beta == meta["beta"]
+    assert sc.base_rate == pytest.approx(meta["base_rate"], rel=1e-12)
+    ids, probs = sc.retrieve(queries, k=10)
+    np.testing.assert_array_equal(ids, arrays["ids_k10"])
+    np.testing.assert_allclose(probs, arrays["probs_k10"], rtol=0, atol=PROB_TOL)
+    off = arrays["dense_nz_off"]
+    for i in range(meta["n_dense"]):
+        dense = sc.get_probabilities(queries[i])
+        nz = np.nonzero(dense)[0]
+        np.testing.assert_array_equal(nz, arrays["dense_nz_idx"][off[i]:off[i + 1]])
+        np.testing.assert_allclose(dense[nz], arrays["dense_nz_val"][off[i]:off[i + 1]], rtol=0, atol=PROB_TOL)
+    # reference edge cases (tests/test_scorer.py:328-344)
+    ids, probs = sc.retrieve([[], ["xyznonexistent"]], k=3)
+    assert probs.shape == (2, 3) and np.all(probs == 0.0)
+    np.testing.assert_array_equal(ids, [[0, 1, 2], [0, 1, 2]])
+    assert np.all(sc.get_probabilities(["xyznonexistent"]) == 0.0)
+    with pytest.raises(NotImplementedError):
+        sc.retrieve(queries[:1], k=3, explain=True)
+    n0 = sc.num_docs
+    sc.add_documents([["term_1", "brandnewtoken"]], show_progress=False)
+    assert sc.num_docs == n0 + 1
+    ids, _ = sc.retrieve([["brandnewtoken"]], k=1)
+    assert ids[0, 0] == n0
+
+
+# ---------------------------------------------------------------------------------
+# batch retrieve vs the oracle on seeded synthetic corpora, all tile sizes
+# ---------------------------------------------------------------------------------
+def _queries_with_edge_cases(vocab, seed):
+    from bayesian_bm25_b200 import synthetic
+    qt, qo = synthetic.zipf_queries(96, vocab, seed)
+    qs = [qt[qo[i]:qo[i + 1]].tolist() for i in range(96)]
+    rng = np.random.default_rng(seed + 1)
+    qs[3] = []                                           # empty query
+    qs[5] = [0, 0, 0]                                    # duplicates of the head term
+    qs[7] = [0, 1, 2, 3, 4]                              # all-head query (loose threshold seed)
+    qs[9] = [vocab - 1]                                  # rarest term only
+    qs[11] = rng.integers(0, vocab, 300).tolist()        # long query, > 255 distinct terms
+    qs[13] = [5, 9, 5, 2, 9, 9, 700 % vocab]             # repeated terms in mixed order
+    qs[95] = []                                          # trailing empty query
+    flat = np.array([t for q in qs for t in q], dtype=np.int32)
+    off = np.cumsum([0] + [len(q) for q in qs]).astype(np.int64)
+    return flat, off
+
+
+@pytest.mark.parametrize("tile_docs", [16384, 8192, 32768])
+def test_retrieve_batch_vs_oracle(tile_docs, monkeypatch):
+    pkg = _pkg()
+    from bayesian_bm25_b200 import synthetic
+    from oracle import coracle
+    monkeypatch.setenv("BB25_TILE_DOCS", str(tile_docs))
+    n_docs, vocab = 150_001, 4000
+    csc = synthetic.zipf_csc(n_docs, vocab, 48.0, seed=21, device=torch.device("cuda:0"))
+    host = _host(csc)
+    sc = pkg.BayesianBM25Scorer(method="lucene", alpha=2.1, beta=0.3, base_rate=0.03)
+    sc.index_from_csc(csc)
+    flat, off = _queries_with_edge_cases(vocab, seed=22)
+    params = coracle.make_params(2.1, 0.3, 0.03)
+    for k in (1, 10, 100, 1000, 4096):
+        ids, scores, probs = sc.retrieve_ids(flat, off, k, return_scores=True)
+        o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
+        np.testing.assert_array_equal(ids, o_ids, err_msg=f"k={k} tile={tile_docs}")
+        np.testing.assert_array_equal(scores.view(np.uint32), o_sc.view(np.uint32))
+        np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
+        assert np.all(np.diff(scores.astype(np.float64), axis=1) <= 0)  # sortedness
+    # dense surfaces
+    for i in (0, 5, 7, 11, 13):
+        q = flat[off[i]:off[i + 1]]
+        np.testing.assert_array_equal(sc.get_scores_ids(q).view(np.uint32), coracle.get_scores(host, q).view(np.uint32))
+        np.testing.assert_allclose(sc.probabilities_device(q).cpu().numpy(), coracle.get_probabilities(host, params, q),
+                                   rtol=0, atol=PROB_TOL)
+    # large-k dense path
+    ids, scores, probs = sc.retrieve_ids(flat[off[0]:off[2]], off[:3] - off[0], 5000, return_scores=True)
+    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat[off[0]:off[2]], off[:3] - off[0], 5000)
+    np.testing.assert_array_equal(ids, o_ids)
+    np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
+
+
+def test_massive_ties_force_threshold_refinement():
+    """Every document holds the same single term with the same value: all N keys tie on
+    the score, the candidate rows overflow and the 64-bit key threshold must converge."""
+    pkg = _pkg()
+    from oracle import coracle
+    n = 70_000
+    csc = {
+        "data": torch.full((n + 3,), 0.5, dtype=torch.float32),
+        "indices": torch.cat([torch.arange(n, dtype=torch.int32), torch.tensor([1, 5, 9], dtype=torch.int32)]),
+        "indptr": torch.tensor([0, n, n + 3], dtype=torch.int64),
+        "doc_len": torch.full((n,), 7, dtype=torch.int32),
+        "num_docs": n, "avgdl": 7.0,
+    }
+    csc["data"][n:] = 0.25
+    sc = pkg.BayesianBM25Scorer(alpha=1.0, beta=0.2)
+    sc.index_from_csc(csc)
+    flat = np.array([0, 0, 1, 1, 0], dtype=np.int32)
+    off = np.array([0, 1, 3, 5], dtype=np.int64)
+    host = _host(csc)
+    params = coracle.make_params(1.0, 0.2, None)
+    for k in (7, 300, 2000):
+        ids, scores, probs = sc.retrieve_ids(flat, off, k, return_scores=True)
+        o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
+        np.testing.assert_array_equal(ids, o_ids)
+        np.testing.assert_array_equal(scores, o_sc)
+        np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
+    assert sc.stats()["rerun_queries"] > 0
+
+
+def test_invalid_inputs_are_rejected():
+    pkg = _pkg()
+    from bayesian_bm25_b200 import _lib, synthetic
+    csc = synthetic.zipf_csc(3000, 200, 20.0, seed=3, device=torch.device("cuda:0"))
+    sc = pkg.BayesianBM25Scorer(alpha=1.0, beta=0.0)
+    sc.index_from_csc(csc)
+    with pytest.raises(ValueError):
+        sc.retrieve_ids(np.array([1], np.int32), np.array([0, 1], np.int64), k=3001)
+    with pytest.raises(RuntimeError, match="out of range"):
+        sc.retrieve_ids(np.array([1, 200], np.int32), np.array([0, 2], np.int64), k=5)
+    with pytest.raises(RuntimeError, match="out of range"):
+        sc.get_scores_ids([999])
+    bad = dict(csc)
+    bad["indices"] = csc["indices"].flip(0).contiguous()
+    with pytest.raises(RuntimeError, match="invalid CSC"):
+        pkg.BayesianBM25Scorer(alpha=1.0, beta=0.0).index_from_csc(bad)
+    before = _lib.lib().bb25_launch_count()
+    sc.retrieve_ids(np.array([1, 2], np.int32), np.array([0, 2], np.int64), k=5)
+    assert _lib.lib().bb25_launch_count() > before
+
+
+# ---------------------------------------------------------------------------------
+# merge, dense top-k, multi-field, block-max
+# ---------------------------------------------------------------------------------
+def test_merge_topk_vs_oracle():
+    from bayesian_bm25_b200 import sharded
+    from oracle import coracle
+    rng = np.random.default_rng(0)
+    for S, Q, k, N in ((8, 33, 1000, 40000), (2, 5, 7, 100), (4, 3, 4096, 20000), (1, 4, 10, 50)):
+        scores = np.round(rng.uniform(0, 2, (Q, N)), 2).astype(np.float32)
+        scores[:, rng.integers(0, N, N // 2)] = 0.0
+        ids = np.empty((S, Q, k), np.int64); sc = np.empty((S, Q, k), np.float32); pr = np.empty((S, Q, k))
+        for s in range(S):
+            lo, hi = s * N // S, (s + 1) * N // S
+            for q in range(Q):
+                i, v = coracle.topk_f32(scores[q, lo:hi], k)
+                ids[s, q], sc[s, q], pr[s, q] = i + lo, v, v * 0.25
+        want = coracle.merge_topk(ids, sc, pr)
+        got = sharded.merge_topk_device(torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda(), torch.from_numpy(pr).cuda())
+        for g_, w_ in zip(got, want):
+            np.testing.assert_array_equal(g_.cpu().numpy(), w_)
+
+
+def test_topk_f64_vs_oracle():
+    from bayesian_bm25_b200 import _lib
+    from oracle import coracle
+    rng = np.random.default_rng(1)
+    cases = [rng.uniform(0, 1, 100_000), np.full(50_000, 7.2e-15), np.round(rng.uniform(0, 1, 200_000), 2),
+             np.concatenate([np.zeros(999), [0.5]]), rng.uniform(0, 1e-300, 5000)]
+    for vals in cases:
+        for k in (1, 10, 1000, min(8192, len(vals))):
+            d = torch.from_numpy(vals).cuda()
+            ids = torch.empty(k, dtype=torch.int64, device="cuda")
+            out = torch.empty(k, dtype=torch.float64, device="cuda")
+            _lib.check(_lib.lib().bb25_topk_f64(0, d.data_ptr(), d.numel(), k, ids.data_ptr(), out.data_ptr(), None))
+            w_ids, w_vals = coracle.topk_f64(vals, k)
+            np.testing.assert_array_equal(ids.cpu().numpy(), w_ids)
+            np.testing.assert_array_equal(out.cpu().numpy(), w_vals)
+
+
+def test_multifield_vs_reference(golden_mf):
+    pkg = _pkg()
+    from oracle import coracle
+    arrays, meta = golden_mf
+    for i, c in enumerate(meta["cases"]):
+        mf = pkg.MultiFieldScorer(["title", "body"], field_weights=c["field_weights"], alpha=c["alpha"],
+                                  base_rate=c["base_rate"], method="lucene")
+        mf.index(meta["docs"], show_progress=False)
+        for f in mf.fields:
+            assert mf._scorers[f].transform.alpha == c["field_alpha"][f]
+            assert mf._scorers[f].transform.beta == c["field_beta"][f]
+        want = arrays[f"mf{i}_probs"]
+        for qi, q in enumerate(meta["queries"]):
+            got = mf.get_probabilities(q)
+            np.testing.assert_allclose(got, want[qi], rtol=1e-9, atol=1e-18)
+            ids, vals = mf.retrieve(q, k=25)
+            w_ids, w_vals = coracle.topk_f64(got, 25)
+            np.testing.assert_array_equal(ids, w_ids)
+            np.testing.assert_array_equal(vals, w_vals)
+    # 1 field == the single scorer (tests/test_multi_field.py:106-129)
+    docs = [{"body": d["body"]} for d in meta["docs"]]
+    mf = pkg.MultiFieldScorer(["body"], method="lucene")
+    mf.index(docs, show_progress=False)
+    single = pkg.BayesianBM25Scorer(method="lucene")
+    single.index([d["body"] for d in docs], show_progress=False)
+    q = meta["queries"][0]
+    fused, alone = mf.get_probabilities(q), single.get_probabilities(q)
+    nzm = alone > 0
+    np.testing.assert_allclose(fused[nzm], alone[nzm], atol=1e-6)
+
+
+def test_blockmax_vs_reference(golden_mf):
+    pkg = _pkg()
+    from bayesian_bm25_b200 import synthetic
+    from oracle import coracle
+    arrays, _ = golden_mf
+    sm = arrays["bmw_matrix"]
+    for bs in (1, 7, 128, 1000, 4096):
+        b = pkg.BlockMaxIndex(block_size=bs)
+        b.build(sm)
+        np.testing.assert_array_equal(b._block_maxes, arrays[f"bmw_bs{bs}"])
+        assert b.n_blocks == -(-sm.shape[1] // bs)
+    b = pkg.BlockMaxIndex(block_size=128)
+    b.build(sm)
+    t = pkg.BayesianProbabilityTransform(1.3, 1.7, base_rate=0.03)
+    got = np.array([[b.bayesian_block_upper_bound(ti, bi, t) for bi in range(b.n_blocks)] for ti in range(2)])
+    np.testing.assert_allclose(got, arrays["bmw_bayes_bs128"][:2], rtol=0, atol=PROB_TOL)
+    with pytest.raises(ValueError, match="2D"):
+        b.build(np.zeros(5))
+    # CSC form + pruning safety: bound >= every document's probability in the block (tests/test_bmw.py:82-113)
+    csc = synthetic.zipf_csc(20_000, 300, 30.0, seed=4, device=torch.device("cuda:0"))
+    sc = pkg.BayesianBM25Scorer(alpha=1.5, beta=0.5, base_rate=0.05)
+    sc.index_from_csc(csc)
+    terms = [0, 3, 50, 299]
+    b.build_from_scorer(sc, terms)
+    want = coracle.blockmax_csc(_host(csc), terms, 128)
+    np.testing.assert_array_equal(b._block_maxes.astype(np.float32), want)
+    probs = sc.probabilities_device([50]).cpu().numpy()
+    bounds = sc.transform.wand_upper_bound(b._block_maxes[2])
+    for blk in range(b.n_blocks):
+        assert probs[blk * 128:(blk + 1) * 128].max() <= bounds[blk] + 1e-15
+
+
+# ---------------------------------------------------------------------------------
+# BASELINE full size (8.8 M docs): direct oracle comparison on a few queries plus
+# size-independent properties (shard union == unsharded, sortedness, dense == top-k)
+# ---------------------------------------------------------------------------------
+def test_full_size_config2_properties():
+    pkg = _pkg()
+    from bayesian_bm25_b200 import index_build, sharded, synthetic
+    from oracle import coracle
+    n_docs, vocab, k = 8_800_000, 30_000, 1000
+    dev = torch.device("cuda:0")
+    csc = synthetic.zipf_csc(n_docs, vocab, 56.0, seed=42, device=dev)
+    nnz = csc["data"].numel()
+    assert 3.9e8 < nnz < 4.3e8  # ~408 M postings
+    sc = pkg.BayesianBM25Scorer(method="lucene", alpha=2.0, beta=0.2, base_rate=0.045)
+    sc.index_from_csc(csc)
+    q_terms, q_off = synthetic.zipf_queries(256, vocab, seed=43)
+    ids, scores, probs = sc.retrieve_ids(q_terms, q_off, k, return_scores=True)
+    assert np.all(np.diff(scores.astype(np.float64), axis=1) <= 0)
+    ties = np.diff(scores.astype(np.float64), axis=1) == 0
+    assert np.all(np.diff(ids, axis=1)[ties] > 0)  # ties by ascending doc id
+    assert np.all((probs >= 0) & (probs <= 1))
+    # oracle on the first queries (CPU, seconds)
+    host = _host(csc)
+    params = coracle.make_params(2.0, 0.2, 0.045)
+    nq = 24
+    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, q_terms[:q_off[nq]], q_off[:nq + 1], k)
+    np.testing.assert_array_equal(ids[:nq], o_ids)
+    np.testing.assert_array_equal(scores[:nq].view(np.uint32), o_sc.view(np.uint32))
+    np.testing.assert_allclose(probs[:nq], o_pr, rtol=0, atol=PROB_TOL)
+    # dense scores agree with the retrieved ones
+    q0 = q_terms[q_off[0]:q_off[1]]
+    dense = sc.get_scores_ids(q0)
+    np.testing.assert_array_equal(dense[ids[0]], scores[0])
+    del host
+    # shard union == unsharded (4 shards scored one after the other on this GPU, merged on device)
+    parts = []
+    dq, do = torch.from_numpy(q_terms).to(dev), torch.from_numpy(q_off).to(dev)
+    for lo, hi in index_build.shard_bounds(n_docs, 4):
+        s = pkg.BayesianBM25Scorer(method="lucene", alpha=2.0, beta=0.2, base_rate=0.045)
+        s.index_from_csc(index_build.shard_csc(csc, lo, hi))
+        parts.append(s.retrieve_ids_device(dq, do, k))
+        del s
+    m_ids, m_sc, m_pr = sharded.merge_topk_device(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]),
+                                                  torch.stack([p[2] for p in parts]))
+    np.testing.assert_array_equal(m_ids.cpu().numpy(), ids)
+    np.testing.assert_array_equal(m_sc.cpu().numpy(), scores)
+    np.testing.assert_array_equal(m_pr.cpu().numpy(), probs)
