@@ -12,6 +12,8 @@
 // Work items are handed out tile-major through a global counter, so all CTAs work on
 // the same one or two tiles for different queries and the tile's slice of the index
 // is served from L2 after its first touch.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "bb25_internal.cuh"
@@ -134,16 +136,74 @@ __device__ __forceinline__ void scatter_slice(const float *__restrict__ data,
     }
 }
 
-template <int D, int NT, int MODE>
-__global__ void __launch_bounds__(NT, (D <= 16384) ? 2 : 1) tile_kernel(const __grid_constant__ TileArgs a) {
+__device__ __forceinline__ int ld_nc_s32(const int32_t *p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_nc_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// Same contract as scatter_slice, different thread -> posting map: every warp-wide
+// load / accumulator update covers 32 CONSECUTIVE postings (128-byte aligned in the
+// main loop).  Doc ids of a dense posting list are (nearly) consecutive, so the
+// shared-memory read-modify-writes of a warp fall into distinct banks, where the
+// 128-bit-per-lane map above puts lanes 4 documents apart (4-way bank conflicts).
+template <int NT, bool COUNT, int U>
+__device__ __forceinline__ void scatter_slice_s32(const float *__restrict__ data,
+                                                  const int32_t *__restrict__ indices, long long s,
+                                                  uint32_t len, float *acc, uint8_t *cnt, int doc_base,
+                                                  int tid) {
+    const long long e = s + (long long)len;
+    long long a0 = (s + 31) & ~31ll;  // first 128-byte aligned element
+    if (a0 > e) a0 = e;
+    if (tid < (int)(a0 - s)) {
+        long long j = s + tid;
+        rmw1<COUNT>(acc, cnt, indices[j] - doc_base, data[j]);
+    }
+    const int n = (int)(e - a0);
+    const int32_t *ip = indices + a0;
+    const float *dp = data + a0;
+    int j = tid;
+    for (; j + (U - 1) * NT < n; j += U * NT) {
+        int d[U];
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            d[u] = ld_nc_s32(ip + j + u * NT);
+            v[u] = ld_nc_f32(dp + j + u * NT);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) rmw1<COUNT>(acc, cnt, d[u] - doc_base, v[u]);
+    }
+    for (; j < n; j += NT) rmw1<COUNT>(acc, cnt, ld_nc_s32(ip + j) - doc_base, ld_nc_f32(dp + j));
+}
+
+// VAR bit 0: strided 32-bit scatter map (else 128-bit per lane)
+// VAR bit 1: retrieve mode keeps no matched-term counters in the tile; the select
+//            kernel recovers tf for the k winners by searching the posting lists
+// resident CTAs per SM the kernel is built for: 5 B/doc of shared memory with counters,
+// 4 B/doc without
+template <int D, int MODE, int VAR>
+constexpr int ctas_per_sm() {
+    return D > 16384 ? 1 : (D > 8192 ? 1 : 2) * (((MODE == MODE_RETRIEVE) && (VAR & 2)) ? 3 : 2);
+}
+
+template <int D, int NT, int MODE, int VAR>
+__global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE, VAR>()) tile_kernel(const __grid_constant__ TileArgs a) {
+    constexpr bool HAS_CNT = (MODE != MODE_RETRIEVE) || !(VAR & 2);
     extern __shared__ __align__(16) unsigned char smem[];
     float *acc = reinterpret_cast<float *>(smem);
     uint8_t *cnt = smem + (size_t)D * 4;
-    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + (size_t)D * 5);
+    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + (size_t)D * (HAS_CNT ? 5 : 4));
     const int tid = threadIdx.x;
 
     for (int i = tid; i < D / 4; i += NT) reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < D / 16; i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
+    if (HAS_CNT)
+        for (int i = tid; i < D / 16; i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
 
     const int n_chunks = (a.n_q + QB - 1) / QB;
     const long long n_items = (long long)(a.tile_end - a.tile_begin) * n_chunks;
@@ -200,8 +260,14 @@ __global__ void __launch_bounds__(NT, (D <= 16384) ? 2 : 1) tile_kernel(const __
                 const uint32_t len = meta->m_len[i];
                 const int flags = meta->m_flags[i];
                 if (len) {
-                    if (flags & 1) scatter_slice<NT, false>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
-                    else scatter_slice<NT, true>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                    const bool count = HAS_CNT && !(flags & 1);
+                    if (VAR & 1) {
+                        if (count) scatter_slice_s32<NT, true, 4>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                        else scatter_slice_s32<NT, false, 4>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                    } else {
+                        if (count) scatter_slice<NT, true>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                        else scatter_slice<NT, false>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                    }
                 }
                 __syncthreads();
                 if (flags & 2) {
@@ -216,11 +282,18 @@ __global__ void __launch_bounds__(NT, (D <= 16384) ? 2 : 1) tile_kernel(const __
                         float4 *acc4 = reinterpret_cast<float4 *>(acc);
                         uint32_t *cnt4 = reinterpret_cast<uint32_t *>(cnt);
                         for (int w = tid; w < D / 4; w += NT) {
-                            const uint32_t c4 = cnt4[w];
-                            if (c4 == 0) continue;  // untouched quad
-                            const float4 v = acc4[w];
+                            uint32_t c4 = 0;
+                            float4 v;
+                            if (HAS_CNT) {
+                                c4 = cnt4[w];
+                                if (c4 == 0) continue;  // untouched quad
+                                v = acc4[w];
+                                cnt4[w] = 0;
+                            } else {
+                                v = acc4[w];
+                                if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+                            }
                             acc4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            cnt4[w] = 0;
                             const float av[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                             for (int c = 0; c < 4; c++) {
@@ -312,7 +385,42 @@ struct SelectArgs {
     float *out_scores;
     double *out_probs;
     unsigned long long *n_cand_total;
+    // tf_search != 0: keys carry no matched-term count; recover it for the winners by
+    // searching each distinct query term's posting list inside the document's tile
+    int tf_search;
+    const int32_t *indices;
+    const int64_t *indptr;
+    const uint32_t *tile_off;
+    int n_tiles, tile_docs;
+    const int32_t *q_terms;
+    const uint8_t *q_nocount;
+    const int64_t *q_off;
+    int64_t term_base;
 };
+
+// scorer.py:592-601 for one (query, document): number of distinct query terms whose
+// posting list contains the document
+__device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t doc) {
+    const long long t0 = a.q_off[q] - a.term_base, t1 = a.q_off[q + 1] - a.term_base;
+    const int tile = (int)(doc / (uint32_t)a.tile_docs);
+    int c = 0;
+    for (long long i = t0; i < t1; i++) {
+        if (a.q_nocount[i]) continue;  // duplicate occurrence of an earlier term
+        const int t = a.q_terms[i];
+        const uint32_t *to = a.tile_off + (size_t)t * (size_t)(a.n_tiles + 1) + tile;
+        const long long base = a.indptr[t];
+        long long lo = base + to[0];
+        const long long end = base + to[1];
+        long long hi = end;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if ((uint32_t)a.indices[mid] < doc) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo < end && (uint32_t)a.indices[lo] == doc) c++;
+    }
+    return c;
+}
 
 template <int NT>
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int P, int tid) {
@@ -383,7 +491,8 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         const size_t o = (size_t)q * (size_t)k + r;
         a.out_ids[o] = (int64_t)id + a.doc_id_offset;
         if (a.out_scores) a.out_scores[o] = sc;
-        a.out_probs[o] = d_doc_probability(a.params, sc, (int)key_tf(key), a.doc_len[id], a.avgdl);
+        const int tf = a.tf_search ? count_matched_terms(a, q, id) : (int)key_tf(key);
+        a.out_probs[o] = d_doc_probability(a.params, sc, tf, a.doc_len[id], a.avgdl);
     }
     if (n_pos < k) {
         // fewer than k matching documents: bm25s fills the tail with zero-score
@@ -423,31 +532,51 @@ __global__ void fill_strided_f64_kernel(double *out, int64_t n, int64_t stride, 
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+// kernel variant (see tile_kernel): BB25_VARIANT=0..3 overrides the default for A/B runs
+static int kernel_variant() {
+    const char *e = getenv("BB25_VARIANT");
+    return (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 3;
+}
+
+template <int DV, int NTV, int MODE, int VAR>
+static int launch_tile_inst(const bb25_index *idx, const TileArgs &a, long long n_items, cudaStream_t st) {
+    constexpr bool has_cnt = (MODE != MODE_RETRIEVE) || !(VAR & 2);
+    const size_t smem = (size_t)DV * (has_cnt ? 5 : 4) + sizeof(TileMeta);
+    BB25_CUDA(cudaFuncSetAttribute(tile_kernel<DV, NTV, MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    int per_sm = ctas_per_sm<DV, MODE, VAR>();
+    if (const char *e = getenv("BB25_CTAS_PER_SM")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= per_sm) per_sm = v;
+    }
+    long long grid = (long long)idx->sm_count * per_sm;
+    if (grid > n_items) grid = n_items;
+    tile_kernel<DV, NTV, MODE, VAR><<<(unsigned)grid, NTV, smem, st>>>(a);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int MODE>
 static int launch_tile(const bb25_index *idx, const TileArgs &a, cudaStream_t st) {
     const int n_chunks = (a.n_q + QB - 1) / QB;
     const long long n_items = (long long)(a.tile_end - a.tile_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-#define BB25_TILE_CASE(DV, NTV)                                                                     \
-    {                                                                                               \
-        const size_t smem = (size_t)DV * 5 + sizeof(TileMeta);                                      \
-        BB25_CUDA(cudaFuncSetAttribute(tile_kernel<DV, NTV, MODE>,                                  \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        const int per_sm = (DV <= 16384) ? 2 : 1;                                                   \
-        long long grid = (long long)idx->sm_count * per_sm;                                         \
-        if (grid > n_items) grid = n_items;                                                         \
-        tile_kernel<DV, NTV, MODE><<<(unsigned)grid, NTV, smem, st>>>(a);                           \
+    const int var = kernel_variant();
+#define BB25_TILE_CASE(DV, NTV)                                                        \
+    switch (var) {                                                                     \
+    case 0: return launch_tile_inst<DV, NTV, MODE, 0>(idx, a, n_items, st);            \
+    case 1: return launch_tile_inst<DV, NTV, MODE, 1>(idx, a, n_items, st);            \
+    case 2: return launch_tile_inst<DV, NTV, MODE, 2>(idx, a, n_items, st);            \
+    default: return launch_tile_inst<DV, NTV, MODE, 3>(idx, a, n_items, st);           \
     }
     switch (idx->tile_docs) {
-    case 8192: BB25_TILE_CASE(8192, 256) break;
-    case 16384: BB25_TILE_CASE(16384, 512) break;
-    case 32768: BB25_TILE_CASE(32768, 1024) break;
+    case 8192: BB25_TILE_CASE(8192, 256)
+    case 16384: BB25_TILE_CASE(16384, 512)
+    case 32768: BB25_TILE_CASE(32768, 1024)
     default: set_error("unsupported tile size %d", idx->tile_docs); return 1;
     }
 #undef BB25_TILE_CASE
-    BB25_LAUNCH_CHECK();
-    return 0;
 }
 
 static void base_args(const bb25_index *idx, TileArgs &a) {
@@ -627,6 +756,16 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.out_scores = out_scores;
     sa.out_probs = out_probs;
     sa.n_cand_total = d_ncand;
+    sa.tf_search = (kernel_variant() & 2) ? 1 : 0;  // same env read as launch_tile within this call
+    sa.indices = idx->indices;
+    sa.indptr = idx->indptr;
+    sa.tile_off = idx->tile_off;
+    sa.n_tiles = idx->n_tiles;
+    sa.tile_docs = idx->tile_docs;
+    sa.q_terms = d_terms;
+    sa.q_nocount = d_nc;
+    sa.q_off = q_off;
+    sa.term_base = term_base;
 
     const size_t sel_smem = (size_t)cap * 9;
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 9));
