@@ -207,7 +207,7 @@ static int pick_tile_docs() {
         int v = atoi(e);
         if (v == 8192 || v == 16384 || v == 32768) return v;
     }
-    return 16384;
+    return 8192;  // 6 resident CTAs x 256 threads per SM in retrieve mode: best measured (profiles/r01)
 }
 
 int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, const float *data,

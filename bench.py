@@ -56,6 +56,9 @@ class ClockSampler:
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:  # let nvidia-smi finish initialising
+                time.sleep(0.05)
         except OSError:
             self.proc = None
 
@@ -143,7 +146,7 @@ def run_reference(args):
     q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, QUERY_SEED)
     from oracle import coracle
     cores = coracle.max_threads()
-    sample = min(args.queries, max(16, 2 * cores))
+    sample = min(args.queries, max(128, 8 * cores))
     for _ in range(args.warmup):
         cpu_baseline(host, q_terms, q_off, args.k, min(sample, cores))
     times = []
@@ -273,7 +276,8 @@ def main():
         torch.cuda.current_stream().synchronize()
         return h_ids.numpy(), h_pr.numpy()
 
-    e2e_step()
+    for _ in range(3):  # lets torch's pinned-host allocator settle on reusable blocks
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -323,7 +327,7 @@ def main():
         if host_csc is not None:
             from oracle import coracle
             cores = coracle.max_threads()
-            sample = args.cpu_sample or min(args.queries, max(32, 2 * cores))
+            sample = args.cpu_sample or min(args.queries, max(128, 8 * cores))
             v, used, dt = cpu_baseline(host_csc, q_terms, q_off, args.k, sample)
             line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": used, "kind": "port",
                                     "sample": f"first {sample} queries of the batch, oracle/bb25_oracle.c, {dt:.1f} s wall"}
