@@ -58,6 +58,38 @@ __global__ void build_tile_table_kernel(const int32_t *__restrict__ indices,
     tile_off[gid] = (uint32_t)(lo - s);
 }
 
+// ---------------------------------------------------------------------------------
+// Block table (see bb25_index::blk_tab).  One CTA walks one term's posting list at a
+// time; entries of empty (block, term) pairs stay {0xFFFFFFFF, 0} -> length 0, never
+// dereferenced.  Pass 0: first-posting offset (min) and block maximum (max of the
+// rounded-up bit pattern; values are >= 0 so bit patterns order like the floats).
+// Pass 1 (after pass 0 finished): posting count into the low 11 bits.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_block_table_kernel(const float *__restrict__ data,
+                                                                const int32_t *__restrict__ indices,
+                                                                const int64_t *__restrict__ indptr,
+                                                                int64_t n_vocab, int pass, uint2 *__restrict__ tab) {
+    for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
+        const int64_t s = indptr[t], e = indptr[t + 1];
+        for (int64_t j = s + threadIdx.x; j < e; j += blockDim.x) {
+            const int b = indices[j] / kBlockDocs;
+            uint2 *ent = tab + (size_t)b * (size_t)n_vocab + (size_t)t;
+            if (pass == 0) {
+                atomicMin(&ent->x, (unsigned int)(j - s));
+                unsigned int bits = __float_as_uint(data[j]);
+                bits = (bits + kBlkLenMask) & ~kBlkLenMask;  // round the bound up, never down
+                atomicMax(&ent->y, bits);
+            } else {
+                atomicAdd(&ent->y, 1u);
+            }
+        }
+    }
+}
+__global__ void init_block_table_kernel(uint2 *tab, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tab[i] = make_uint2(0xFFFFFFFFu, 0u);
+}
+
 // Input validation on device: column starts monotone, doc ids in range and strictly
 // ascending inside a column, posting values >= 0 and not NaN.  flags[0] |= bit.
 __global__ void validate_csc_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
@@ -288,6 +320,20 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
         TRY(cudaGetLastError());
         TRY(cudaDeviceSynchronize());
     }
+    {
+        idx->n_blocks = (int)((n_docs + kBlockDocs - 1) / kBlockDocs);
+        const size_t ne = (size_t)idx->n_blocks * (size_t)n_vocab;
+        TRY(cudaMalloc(&idx->blk_tab, ne * sizeof(uint2)));
+        idx->device_bytes += ne * sizeof(uint2);
+        init_block_table_kernel<<<(unsigned)((ne + 255) / 256), 256>>>(idx->blk_tab, ne);
+        const int grid = (int)(n_vocab < (int64_t)idx->sm_count * 16 ? n_vocab : (int64_t)idx->sm_count * 16);
+        build_block_table_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, 0, idx->blk_tab);
+        build_block_table_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, 1, idx->blk_tab);
+        count_launch(3);
+        TRY(cudaGetLastError());
+        TRY(cudaDeviceSynchronize());
+        if (const char *e = getenv("BB25_PRUNE")) idx->prune = atoi(e) ? 1 : 0;
+    }
 #undef TRY
     *out = idx;
     return 0;
@@ -303,6 +349,7 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->indptr);
     cudaFree(idx->doc_len);
     cudaFree(idx->tile_off);
+    cudaFree(idx->blk_tab);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
     if (idx->ws) cudaFree(idx->ws);
     if (idx->pinned) cudaFreeHost(idx->pinned);

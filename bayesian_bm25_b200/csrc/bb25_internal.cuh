@@ -51,6 +51,8 @@ struct DeviceGuard {
 };
 
 constexpr double kEps = 1e-10;  // probability.py:20
+constexpr int kBlockDocs = 1024;  // documents per warp-private block
+constexpr uint32_t kBlkLenMask = 0x7FFu;
 
 // ---- probability.py / fusion.py scalar math, fp64 -------------------------------
 __host__ __device__ inline double clamp_prob(double p) {  // probability.py:24-26
@@ -125,6 +127,12 @@ struct bb25_index {
     int tile_docs = 0;  // docs per traversal tile (shared-memory accumulator span)
     int n_tiles = 0;
     uint32_t *tile_off = nullptr;  // [n_vocab][n_tiles+1] offsets relative to indptr[t]
+    // block table for the warp-private traversal: [n_blocks][n_vocab] entries
+    //   .x = offset of term t's first posting in block b, relative to indptr[t]
+    //   .y = (fp32 bits of the block maximum, rounded UP to a multiple of 2^11) | posting count (<= 1024)
+    uint2 *blk_tab = nullptr;
+    int n_blocks = 0;
+    int prune = 1;  // skip (block, query) units whose block-max bound is below the query threshold
     std::map<int, float *> kth_cache;  // k -> fp32[n_vocab] k-th largest posting value per term
     // grow-only device workspace shared by query calls (serialised by mu)
     std::mutex mu;
@@ -134,6 +142,7 @@ struct bb25_index {
     size_t device_bytes = 0;
     // stats of the last retrieve_batch
     int64_t st_launches = 0, st_passes = 0, st_reruns = 0, st_candidates = 0;
+    int64_t st_units = 0, st_units_skipped = 0;  // (block, query) units visited / pruned
     // CUDA-event pairs around the traversal launches of the last retrieve_batch
     static constexpr int kMaxEv = 256;
     cudaEvent_t ev[2 * kMaxEv] = {};

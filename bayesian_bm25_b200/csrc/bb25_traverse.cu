@@ -524,6 +524,251 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     }
 }
 
+
+// =================================================================================
+// Warp-private traversal (retrieve mode).  A BLOCK = 1024 consecutive documents whose
+// fp32 accumulators (4 KB) belong to ONE warp; a warp pulls (block, 16-query chunk)
+// items from a global counter and, for every query of the chunk,
+//   1. reads the block-table entries of the query's terms (offset, length, block max),
+//   2. forms the block's score upper bound in query order and SKIPS the unit when the
+//      bound is below the query's threshold (block-max pruning; exact because fp32
+//      addition of non-negative values is monotone), or when no term has a posting
+//      in the block,
+//   3. otherwise adds the terms' posting slices in query order (a __syncwarp between
+//      terms is all the ordering needs: one warp owns every document of the block),
+//   4. scans its 1024 accumulators, emits keys >= threshold and zeroes them.
+// No block-level barrier anywhere; 48 resident warps per SM hide each other's L2
+// latency.  Items are block-major, so the whole chip works on a handful of adjacent
+// blocks whose index slices sit in L2.
+// =================================================================================
+constexpr int QC = 16;       // queries per warp work item
+constexpr int BK_WARPS = 8;  // warps per CTA (6 CTAs/SM -> 48 warps, 192 KB of accumulators)
+
+struct BlockArgs {
+    const float *data;
+    const int32_t *indices;
+    const int64_t *indptr;
+    const uint2 *blk_tab;
+    int64_t n_vocab;
+    const int32_t *q_terms;  // sanitised copy, indexed by absolute position - term_base
+    const int64_t *q_off;
+    int64_t term_base;
+    const int32_t *q_list;
+    int n_q;
+    int blk_begin, blk_end;
+    const unsigned long long *thr;
+    unsigned int *cand_cnt;
+    unsigned long long *cand_key;
+    int cap;
+    int prune;
+    unsigned long long *work_counter;
+    unsigned long long *stats;  // [0] units visited, [1] units pruned by the block-max bound
+};
+
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+    int lo = __shfl_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), src);
+    int hi = __shfl_sync(0xFFFFFFFFu, (int)(v >> 32), src);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+
+// postings [s, s+len) of one term, len <= 1024, into the warp's block accumulators
+__device__ __forceinline__ void scatter_warp(const float *__restrict__ data, const int32_t *__restrict__ indices,
+                                             long long s, int len, float *acc, int doc_base, int lane) {
+    int head = (int)((32 - (s & 31)) & 31);  // elements before the first 128-byte boundary
+    if (head > len) head = len;
+    if (lane < head) {
+        const long long j = s + lane;
+        const int o = ld_nc_s32(indices + j) - doc_base;
+        acc[o] = __fadd_rn(acc[o], ld_nc_f32(data + j));
+    }
+    const int n = len - head;
+    const int32_t *ip = indices + s + head;
+    const float *dp = data + s + head;
+    int j = lane;
+    for (; j + 96 < n; j += 128) {
+        int d[4];
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            d[u] = ld_nc_s32(ip + j + 32 * u);
+            v[u] = ld_nc_f32(dp + j + 32 * u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int o = d[u] - doc_base;
+            acc[o] = __fadd_rn(acc[o], v[u]);
+        }
+    }
+    for (; j < n; j += 32) {
+        const int o = ld_nc_s32(ip + j) - doc_base;
+        acc[o] = __fadd_rn(acc[o], ld_nc_f32(dp + j));
+    }
+}
+
+struct TermEnt {
+    long long start;
+    int len;
+    float bmax;
+};
+
+__device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uint2 *row, long long pos, bool active) {
+    TermEnt e;
+    e.start = 0;
+    e.len = 0;
+    e.bmax = 0.f;
+    if (active) {
+        const int t = a.q_terms[pos];
+        const uint2 ent = row[t];
+        e.len = (int)(ent.y & kBlkLenMask);
+        e.bmax = __uint_as_float(ent.y & ~kBlkLenMask);
+        e.start = a.indptr[t] + (long long)ent.x;
+    }
+    return e;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 6) block_kernel(const __grid_constant__ BlockArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float *acc = reinterpret_cast<float *>(smem) + warp * kBlockDocs;
+    float4 *acc4 = reinterpret_cast<float4 *>(acc);
+    for (int i = lane; i < kBlockDocs / 4; i += 32) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    const int n_chunks = (a.n_q + QC - 1) / QC;
+    const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
+    unsigned long long n_units = 0, n_skipped = 0;
+
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ull);
+        item = shfl_ll(item, 0);
+        if (item >= n_items) break;
+        const int blk = a.blk_begin + (int)(item / n_chunks);
+        const int slot0 = (int)(item % n_chunks) * QC;
+        const int nslots = min(QC, a.n_q - slot0);
+        const int doc_base = blk * kBlockDocs;
+        const uint2 *row = a.blk_tab + (size_t)blk * (size_t)a.n_vocab;
+
+        // lane s holds the description of the chunk's s-th query
+        int my_q = 0, my_m = 0;
+        long long my_t0 = 0;
+        unsigned long long my_thr = 0;
+        if (lane < nslots) {
+            my_q = a.q_list ? a.q_list[slot0 + lane] : slot0 + lane;
+            const long long t0 = a.q_off[my_q];
+            my_m = (int)max(0ll, (long long)a.q_off[my_q + 1] - t0);
+            my_t0 = t0 - a.term_base;
+            my_thr = a.thr[my_q];
+        }
+
+        for (int sidx = 0; sidx < nslots; sidx++) {
+            const int m = __shfl_sync(0xFFFFFFFFu, my_m, sidx);
+            if (m == 0) continue;
+            const int q = __shfl_sync(0xFFFFFFFFu, my_q, sidx);
+            const long long t0 = shfl_ll(my_t0, sidx);
+            const unsigned long long thr = (unsigned long long)shfl_ll((long long)my_thr, sidx);
+            const uint32_t thr_score = (uint32_t)(thr >> 33);
+            n_units++;
+
+            if (m <= 32) {
+                const TermEnt e = load_term_entry(a, row, t0 + lane, lane < m);
+                if (__ballot_sync(0xFFFFFFFFu, e.len > 0) == 0u) continue;  // no posting of any term in this block
+                float ub = 0.f;
+                for (int i = 0; i < m; i++) ub = __fadd_rn(ub, __shfl_sync(0xFFFFFFFFu, e.bmax, i));
+                if (a.prune && __float_as_uint(ub) < thr_score) {
+                    n_skipped++;
+                    continue;
+                }
+                for (int i = 0; i < m; i++) {
+                    const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
+                    const long long s = shfl_ll(e.start, i);
+                    if (len) scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                    __syncwarp();
+                }
+            } else {
+                // long query: bound first (one pass over the entries), then the adds
+                float ub = 0.f;
+                unsigned any = 0u;
+                for (int b0 = 0; b0 < m; b0 += 32) {
+                    const int nb = min(32, m - b0);
+                    const TermEnt e = load_term_entry(a, row, t0 + b0 + lane, lane < nb);
+                    any |= __ballot_sync(0xFFFFFFFFu, e.len > 0);
+                    for (int i = 0; i < nb; i++) ub = __fadd_rn(ub, __shfl_sync(0xFFFFFFFFu, e.bmax, i));
+                }
+                if (any == 0u) continue;
+                if (a.prune && __float_as_uint(ub) < thr_score) {
+                    n_skipped++;
+                    continue;
+                }
+                for (int b0 = 0; b0 < m; b0 += 32) {
+                    const int nb = min(32, m - b0);
+                    const TermEnt e = load_term_entry(a, row, t0 + b0 + lane, lane < nb);
+                    for (int i = 0; i < nb; i++) {
+                        const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
+                        const long long s = shfl_ll(e.start, i);
+                        if (len) scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                        __syncwarp();
+                    }
+                }
+            }
+
+            // fused epilogue over the warp's 1024 accumulators
+            unsigned int *ccnt = a.cand_cnt + q;
+            unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
+            for (int w = lane; w < kBlockDocs / 4; w += 32) {
+                const float4 v = acc4[w];
+                if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+                acc4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float av[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t bits = __float_as_uint(av[c]);
+                    if (bits != 0u && bits >= thr_score) {
+                        const unsigned long long key = make_key(bits, (uint32_t)(doc_base + w * 4 + c), 0u);
+                        if (key >= thr) {
+                            const unsigned int pos = atomicAdd(ccnt, 1u);
+                            if (pos < (unsigned)a.cap) crow[pos] = key;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && a.stats) {
+        atomicAdd(&a.stats[0], n_units);
+        atomicAdd(&a.stats[1], n_skipped);
+    }
+}
+
+static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t st) {
+    const int n_chunks = (a.n_q + QC - 1) / QC;
+    const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
+    if (n_items <= 0) return 0;
+    BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+    const size_t smem = (size_t)BK_WARPS * kBlockDocs * sizeof(float);
+    BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 6;
+    if (const char *e = getenv("BB25_CTAS_PER_SM")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 6) per_sm = v;
+    }
+    long long grid = (long long)idx->sm_count * per_sm;
+    const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
+    if (grid > need) grid = need;
+    block_kernel<BK_WARPS><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+// traversal kernel family used by retrieve: BB25_KERNEL=tile selects the CTA-tile kernel
+static bool use_block_kernel() {
+    const char *e = getenv("BB25_KERNEL");
+    return !(e && e[0] == 't');
+}
+
 __global__ void fill_strided_f64_kernel(double *out, int64_t n, int64_t stride, double v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i * stride] = v;
@@ -695,6 +940,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     unsigned int *d_nover = (unsigned int *)(ws + o_ctr + 8);
     int *d_err = (int *)(ws + o_ctr + 16);
     unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
+    unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [2]
     unsigned long long *d_keys = (unsigned long long *)(ws + o_key);
 
     const float *kth = nullptr;
@@ -712,9 +958,10 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
 
     // tile groups: a small first group makes a loose threshold seed cheap to repair,
     // later groups run with the exact k-th key of everything seen so far
+    const bool blockk = use_block_kernel();
     int bounds[4];
     int ng = 0;
-    const int T = idx->n_tiles;
+    const int T = blockk ? idx->n_blocks : idx->n_tiles;
     bounds[0] = 0;
     if (T >= 16) {
         bounds[1] = std::max(1, T / 16);
@@ -739,6 +986,23 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ta.params = *params;
     ta.work_counter = d_work;
 
+    BlockArgs ba{};
+    ba.data = idx->data;
+    ba.indices = idx->indices;
+    ba.indptr = idx->indptr;
+    ba.blk_tab = idx->blk_tab;
+    ba.n_vocab = idx->n_vocab;
+    ba.q_terms = d_terms;
+    ba.q_off = q_off;
+    ba.term_base = term_base;
+    ba.thr = d_thr;
+    ba.cand_cnt = d_cnt;
+    ba.cand_key = d_keys;
+    ba.cap = cap;
+    ba.prune = idx->prune;
+    ba.work_counter = d_work;
+    ba.stats = d_stats;
+
     SelectArgs sa{};
     sa.cand_cnt = d_cnt;
     sa.n_prev = d_prev;
@@ -756,7 +1020,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.out_scores = out_scores;
     sa.out_probs = out_probs;
     sa.n_cand_total = d_ncand;
-    sa.tf_search = (kernel_variant() & 2) ? 1 : 0;  // same env read as launch_tile within this call
+    sa.tf_search = (blockk || (kernel_variant() & 2)) ? 1 : 0;  // keys carry no tf in those kernels
     sa.indices = idx->indices;
     sa.indptr = idx->indptr;
     sa.tile_off = idx->tile_off;
@@ -789,7 +1053,15 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
                 }
                 BB25_CUDA(cudaEventRecord(idx->ev[2 * pair], st));
             }
-            if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) return 1;
+            if (blockk) {
+                ba.q_list = cur_list;
+                ba.n_q = cur_n;
+                ba.blk_begin = bounds[gi];
+                ba.blk_end = bounds[gi + 1];
+                if (launch_block(idx, ba, st)) return 1;
+            } else if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) {
+                return 1;
+            }
             if (pair >= 0) {
                 BB25_CUDA(cudaEventRecord(idx->ev[2 * pair + 1], st));
                 idx->ev_used++;
@@ -816,11 +1088,12 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
             flip ^= 1;
         }
     }
-    unsigned long long h_ncand = 0;
-    BB25_CUDA(cudaMemcpyAsync(idx->pinned, d_ncand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaMemcpyAsync(idx->pinned, d_ncand, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     BB25_CUDA(cudaStreamSynchronize(st));
-    h_ncand = *(unsigned long long *)idx->pinned;
-    idx->st_candidates = (int64_t)h_ncand;
+    const unsigned long long *h_c = (const unsigned long long *)idx->pinned;
+    idx->st_candidates = (int64_t)h_c[0];
+    idx->st_units = (int64_t)h_c[1];
+    idx->st_units_skipped = (int64_t)h_c[2];
     for (int i = 0; i < idx->ev_used; i++) {
         float ms = 0.f;
         BB25_CUDA(cudaEventElapsedTime(&ms, idx->ev[2 * i], idx->ev[2 * i + 1]));
@@ -926,6 +1199,20 @@ int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passe
     if (passes) *passes = idx->st_passes;
     if (rerun_queries) *rerun_queries = idx->st_reruns;
     if (candidates) *candidates = idx->st_candidates;
+    return 0;
+}
+
+int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (units) *units = idx->st_units;
+    if (units_skipped) *units_skipped = idx->st_units_skipped;
+    return 0;
+}
+
+int bb25_index_set_pruning(bb25_index *idx, int enable) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->prune = enable ? 1 : 0;
     return 0;
 }
 

@@ -377,4 +377,12 @@ class BayesianBM25Scorer:
         ms, nl = C.c_double(), C.c_int64()
         _lib.check(_lib.lib().bb25_retrieve_timing(self._handle, C.byref(ms), C.byref(nl)))
         out["traverse_ms"], out["traverse_launches"] = ms.value, nl.value
+        u, sk = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().bb25_retrieve_prune_stats(self._handle, C.byref(u), C.byref(sk)))
+        out["units"], out["units_skipped"] = u.value, sk.value
         return out
+
+    def set_pruning(self, enable: bool) -> None:
+        """Block-max pruning of (block, query) units in batch retrieve (exact either way)."""
+        self._require_index("set_pruning()")
+        _lib.check(_lib.lib().bb25_index_set_pruning(self._handle, int(bool(enable))))

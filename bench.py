@@ -241,7 +241,7 @@ def main():
         sampler.start()
     launches0 = _lib.lib().bb25_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    trav_ms, trav_launches, reruns = 0.0, 0, 0
+    trav_ms, trav_launches, reruns, units, skipped = 0.0, 0, 0, 0, 0
     barrier()
     ev0.record()
     for _ in range(args.steps):
@@ -250,6 +250,8 @@ def main():
         trav_ms += st["traverse_ms"]
         trav_launches += st["traverse_launches"]
         reruns += st["rerun_queries"]
+        units += st["units"]
+        skipped += st["units_skipped"]
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -309,6 +311,9 @@ def main():
                 "cache": "inputs larger than L2 (CSC index %.2f GB per GPU, 126 MB L2)" % (nnz_full * 8 / world / 1e9),
                 "probabilities": "fp64 posterior fused on device", "index_build_s": round(t_build, 1),
                 "threshold_reruns_per_step": reruns / args.steps,
+                "kernel": os.environ.get("BB25_KERNEL", "block"),
+                "pruning": {"enabled": os.environ.get("BB25_PRUNE", "1") != "0", "block_docs": 1024,
+                            "units_per_step": units / args.steps, "units_skipped_per_step": skipped / args.steps},
             },
             "clocks": clocks,
             "e2e": {"value": args.queries * args.steps / e2e_s, "unit": "queries/s",

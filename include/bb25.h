@@ -125,6 +125,14 @@ int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const i
 int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passes,
                         int64_t *rerun_queries, int64_t *candidates);
 
+/* Block-max pruning (north star item 4).  The batch traversal works on 1024-document
+ * blocks; a (block, query) unit whose block-max score bound (BlockMaxIndex semantics,
+ * scorer.py:55-99, summed in query order) is below the query's current top-k threshold
+ * cannot contribute and is skipped.  Results are identical with pruning on or off.
+ * Default: on.  bb25_retrieve_prune_stats: units visited / skipped in the last batch. */
+int bb25_index_set_pruning(bb25_index *idx, int enable);
+int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped);
+
 /* Device time of the traversal kernel in the last bb25_retrieve_batch on this handle,
  * measured with CUDA events on the call's stream around every traversal launch
  * (sum over launches, and their number).  Used for the roofline figure. */

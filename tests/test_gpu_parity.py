@@ -190,11 +190,16 @@ def _queries_with_edge_cases(vocab, seed):
     return flat, off
 
 
-@pytest.mark.parametrize("tile_docs", [16384, 8192, 32768])
-def test_retrieve_batch_vs_oracle(tile_docs, monkeypatch):
+@pytest.mark.parametrize("kernel,tile_docs,prune", [
+    ("block", 8192, 1), ("block", 8192, 0), ("tile", 8192, 1), ("tile", 16384, 1), ("tile", 32768, 1)])
+def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
+    """Both traversal kernels (warp-private blocks with and without block-max pruning,
+    CTA tiles at every tile size) must give the oracle's result bit for bit."""
     pkg = _pkg()
     from bayesian_bm25_b200 import synthetic
     from oracle import coracle
+    monkeypatch.setenv("BB25_KERNEL", kernel)
+    monkeypatch.setenv("BB25_PRUNE", str(prune))
     monkeypatch.setenv("BB25_TILE_DOCS", str(tile_docs))
     n_docs, vocab = 150_001, 4000
     csc = synthetic.zipf_csc(n_docs, vocab, 48.0, seed=21, device=torch.device("cuda:0"))
@@ -206,10 +211,17 @@ def test_retrieve_batch_vs_oracle(tile_docs, monkeypatch):
     for k in (1, 10, 100, 1000, 4096):
         ids, scores, probs = sc.retrieve_ids(flat, off, k, return_scores=True)
         o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
-        np.testing.assert_array_equal(ids, o_ids, err_msg=f"k={k} tile={tile_docs}")
+        np.testing.assert_array_equal(ids, o_ids, err_msg=f"k={k} kernel={kernel} tile={tile_docs} prune={prune}")
         np.testing.assert_array_equal(scores.view(np.uint32), o_sc.view(np.uint32))
         np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
         assert np.all(np.diff(scores.astype(np.float64), axis=1) <= 0)  # sortedness
+        st = sc.stats()
+        if kernel == "block":
+            assert st["units"] > 0
+            if prune == 0:
+                assert st["units_skipped"] == 0, st
+            elif k == 1:
+                assert st["units_skipped"] > 0, st  # a top-1 threshold prunes most blocks
     # dense surfaces
     for i in (0, 5, 7, 11, 13):
         q = flat[off[i]:off[i + 1]]
