@@ -255,13 +255,15 @@ def test_massive_ties_force_threshold_refinement():
     off = np.array([0, 1, 3, 5], dtype=np.int64)
     host = _host(csc)
     params = coracle.make_params(1.0, 0.2, None)
+    reruns = 0
     for k in (7, 300, 2000):
         ids, scores, probs = sc.retrieve_ids(flat, off, k, return_scores=True)
         o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
         np.testing.assert_array_equal(ids, o_ids)
         np.testing.assert_array_equal(scores, o_sc)
         np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
-    assert sc.stats()["rerun_queries"] > 0
+        reruns += sc.stats()["rerun_queries"]
+    assert reruns > 0  # at least one candidate row overflowed and was repaired
 
 
 def test_invalid_inputs_are_rejected():
