@@ -4,7 +4,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <utility>
+#include <vector>
 
 #include "bb25_internal.cuh"
 
@@ -84,6 +87,18 @@ __global__ void __launch_bounds__(256) build_block_table_kernel(const float *__r
             }
         }
     }
+}
+// dense_vals[slot][doc] = value of the slot's term in doc (0.0f where absent)
+__global__ void __launch_bounds__(256) build_dense_rows_kernel(const float *__restrict__ data,
+                                                               const int32_t *__restrict__ indices,
+                                                               const int64_t *__restrict__ indptr,
+                                                               const int32_t *__restrict__ terms, int64_t stride,
+                                                               float *__restrict__ dense) {
+    const int32_t t = terms[blockIdx.y];
+    const int64_t s = indptr[t], e = indptr[t + 1];
+    float *row = dense + (int64_t)blockIdx.y * stride;
+    for (int64_t j = s + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (int64_t)gridDim.x * blockDim.x)
+        row[indices[j]] = data[j];
 }
 __global__ void init_block_table_kernel(uint2 *tab, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,7 +347,49 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
         count_launch(3);
         TRY(cudaGetLastError());
         TRY(cudaDeviceSynchronize());
-        if (const char *e = getenv("BB25_PRUNE")) idx->prune = atoi(e) ? 1 : 0;
+        if (const char *e = getenv("BB25_PRUNE")) {
+            const int v = atoi(e);
+            idx->prune = v < 0 ? 0 : (v > 2 ? 2 : v);
+        }
+    }
+    {
+        // dense value rows for the head terms
+        std::vector<int64_t> h_indptr((size_t)n_vocab + 1);
+        TRY(cudaMemcpy(h_indptr.data(), idx->indptr, h_indptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        std::vector<std::pair<int64_t, int32_t>> cand;
+        for (int64_t t = 0; t < n_vocab; t++) {
+            const int64_t df = h_indptr[t + 1] - h_indptr[t];
+            if (df > 0 && df * 8 >= n_docs) cand.emplace_back(-df, (int32_t)t);
+        }
+        std::sort(cand.begin(), cand.end());
+        if ((int)cand.size() > kMaxDenseTerms) cand.resize(kMaxDenseTerms);
+        std::vector<int32_t> h_slot((size_t)n_vocab, -1);
+        std::vector<int32_t> h_terms;
+        for (size_t i = 0; i < cand.size(); i++) {
+            h_slot[cand[i].second] = (int32_t)i;
+            h_terms.push_back(cand[i].second);
+        }
+        idx->n_dense = (int)cand.size();
+        idx->dense_stride = (int64_t)idx->n_blocks * kBlockDocs;
+        TRY(cudaMalloc(&idx->dense_slot, (size_t)n_vocab * sizeof(int32_t)));
+        TRY(cudaMemcpy(idx->dense_slot, h_slot.data(), (size_t)n_vocab * sizeof(int32_t), cudaMemcpyHostToDevice));
+        idx->device_bytes += (size_t)n_vocab * sizeof(int32_t);
+        if (idx->n_dense > 0) {
+            const size_t nb = (size_t)idx->n_dense * (size_t)idx->dense_stride * sizeof(float);
+            TRY(cudaMalloc(&idx->dense_vals, nb));
+            TRY(cudaMemset(idx->dense_vals, 0, nb));
+            idx->device_bytes += nb;
+            int32_t *d_terms = nullptr;
+            TRY(cudaMalloc(&d_terms, h_terms.size() * sizeof(int32_t)));
+            TRY(cudaMemcpy(d_terms, h_terms.data(), h_terms.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            dim3 grid(128, (unsigned)idx->n_dense);
+            build_dense_rows_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, d_terms, idx->dense_stride,
+                                                   idx->dense_vals);
+            count_launch();
+            TRY(cudaGetLastError());
+            TRY(cudaDeviceSynchronize());
+            cudaFree(d_terms);
+        }
     }
 #undef TRY
     *out = idx;
@@ -350,6 +407,8 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->doc_len);
     cudaFree(idx->tile_off);
     cudaFree(idx->blk_tab);
+    cudaFree(idx->dense_slot);
+    cudaFree(idx->dense_vals);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
     if (idx->ws) cudaFree(idx->ws);
     if (idx->pinned) cudaFreeHost(idx->pinned);

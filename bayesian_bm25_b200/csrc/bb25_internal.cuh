@@ -53,6 +53,7 @@ struct DeviceGuard {
 constexpr double kEps = 1e-10;  // probability.py:20
 constexpr int kBlockDocs = 1024;  // documents per warp-private block
 constexpr uint32_t kBlkLenMask = 0x7FFu;
+constexpr int kMaxDenseTerms = 64;
 
 // ---- probability.py / fusion.py scalar math, fp64 -------------------------------
 __host__ __device__ inline double clamp_prob(double p) {  // probability.py:24-26
@@ -132,7 +133,14 @@ struct bb25_index {
     //   .y = (fp32 bits of the block maximum, rounded UP to a multiple of 2^11) | posting count (<= 1024)
     uint2 *blk_tab = nullptr;
     int n_blocks = 0;
-    int prune = 1;  // skip (block, query) units whose block-max bound is below the query threshold
+    int prune = 2;  // 0 exhaustive, 1 skip (block, query) units under the block-max bound, 2 + MaxScore units
+    // dense value rows for the most frequent terms (df >= n_docs/8, at most kMaxDenseTerms):
+    // dense_vals[slot][doc] = posting value or 0.0f; O(1) lookup of a head term's
+    // contribution to one document, used by the MaxScore path of the block kernel
+    int32_t *dense_slot = nullptr;  // [n_vocab] slot or -1
+    float *dense_vals = nullptr;    // [n_dense][dense_stride]
+    int n_dense = 0;
+    int64_t dense_stride = 0;       // n_blocks * kBlockDocs
     std::map<int, float *> kth_cache;  // k -> fp32[n_vocab] k-th largest posting value per term
     // grow-only device workspace shared by query calls (serialised by mu)
     std::mutex mu;
@@ -142,7 +150,7 @@ struct bb25_index {
     size_t device_bytes = 0;
     // stats of the last retrieve_batch
     int64_t st_launches = 0, st_passes = 0, st_reruns = 0, st_candidates = 0;
-    int64_t st_units = 0, st_units_skipped = 0;  // (block, query) units visited / pruned
+    int64_t st_units = 0, st_units_skipped = 0, st_units_maxscore = 0;  // (block, query) units visited / pruned / MaxScore
     // CUDA-event pairs around the traversal launches of the last retrieve_batch
     static constexpr int kMaxEv = 256;
     cudaEvent_t ev[2 * kMaxEv] = {};

@@ -560,10 +560,20 @@ struct BlockArgs {
     unsigned int *cand_cnt;
     unsigned long long *cand_key;
     int cap;
-    int prune;
+    int prune;  // 0 exhaustive, 1 block-max skip, 2 block-max skip + MaxScore units
+    const int32_t *dense_slot;
+    const float *dense_vals;
+    int64_t dense_stride;
     unsigned long long *work_counter;
-    unsigned long long *stats;  // [0] units visited, [1] units pruned by the block-max bound
+    unsigned long long *stats;  // [0] units visited, [1] pruned by the block-max bound, [2] MaxScore units
 };
+
+// per-warp shared memory: 1024 fp32 accumulators [+ candidate list u16[512] + bitmap u32[32]]
+constexpr int kMsListCap = 512;
+template <bool MS>
+__host__ __device__ constexpr int warp_smem_bytes() {
+    return kBlockDocs * 4 + (MS ? kMsListCap * 2 + 128 : 0);
+}
 
 __device__ __forceinline__ long long shfl_ll(long long v, int src) {
     int lo = __shfl_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), src);
@@ -609,6 +619,7 @@ struct TermEnt {
     long long start;
     int len;
     float bmax;
+    int term;
 };
 
 __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uint2 *row, long long pos, bool active) {
@@ -616,9 +627,11 @@ __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uin
     e.start = 0;
     e.len = 0;
     e.bmax = 0.f;
+    e.term = 0;
     if (active) {
         const int t = a.q_terms[pos];
         const uint2 ent = row[t];
+        e.term = t;
         e.len = (int)(ent.y & kBlkLenMask);
         e.bmax = __uint_as_float(ent.y & ~kBlkLenMask);
         e.start = a.indptr[t] + (long long)ent.x;
@@ -626,19 +639,43 @@ __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uin
     return e;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 6) block_kernel(const __grid_constant__ BlockArgs a) {
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+// emit one accumulator if it can enter the query's top-k
+__device__ __forceinline__ void emit_if_candidate(float v, uint32_t local_id, uint32_t thr_score,
+                                                  unsigned long long thr, unsigned int *ccnt,
+                                                  unsigned long long *crow, int cap) {
+    const uint32_t bits = __float_as_uint(v);
+    if (bits != 0u && bits >= thr_score) {
+        const unsigned long long key = make_key(bits, local_id, 0u);
+        if (key >= thr) {
+            const unsigned int pos = atomicAdd(ccnt, 1u);
+            if (pos < (unsigned)cap) crow[pos] = key;
+        }
+    }
+}
+
+template <int WARPS, bool MS>
+__global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *acc = reinterpret_cast<float *>(smem) + warp * kBlockDocs;
+    unsigned char *wbase = smem + (size_t)warp * warp_smem_bytes<MS>();
+    float *acc = reinterpret_cast<float *>(wbase);
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
+    uint16_t *clist = reinterpret_cast<uint16_t *>(wbase + kBlockDocs * 4);
+    unsigned int *cbm = reinterpret_cast<unsigned int *>(wbase + kBlockDocs * 4 + kMsListCap * 2);
     for (int i = lane; i < kBlockDocs / 4; i += 32) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MS) cbm[lane] = 0u;
     __syncwarp();
 
     const int n_chunks = (a.n_q + QC - 1) / QC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
-    unsigned long long n_units = 0, n_skipped = 0;
+    unsigned long long n_units = 0, n_skipped = 0, n_ms = 0;
 
     for (;;) {
         long long item = 0;
@@ -680,6 +717,101 @@ __global__ void __launch_bounds__(WARPS * 32, 6) block_kernel(const __grid_const
                 if (a.prune && __float_as_uint(ub) < thr_score) {
                     n_skipped++;
                     continue;
+                }
+                if (MS && a.prune >= 2 && thr_score != 0u) {
+                    // ---- MaxScore split of the query's terms for this block -------------------
+                    // NE ("non-essential"): head terms with a dense value row whose block maxima,
+                    // summed, stay below the threshold: a document holding only NE terms cannot
+                    // qualify.  Everything else (S) is scattered as usual; NE values are then
+                    // GATHERED only for documents some S term touched.  The NE bound is summed in
+                    // ascending order with a 1e-5 relative margin, which dominates the rounding
+                    // difference to any other summation order (m <= 32 terms).
+                    const int dslot = (lane < m && e.len > 0) ? a.dense_slot[e.term] : -1;
+                    const float thr_val = __uint_as_float(thr_score);
+                    unsigned rem = __ballot_sync(0xFFFFFFFFu, dslot >= 0);
+                    unsigned ne_mask = 0u;
+                    float run = 0.f;
+                    while (rem) {
+                        float best = 0.f;
+                        int bl = -1;
+                        for (unsigned mm = rem; mm; mm &= mm - 1) {
+                            const int L = __ffs(mm) - 1;
+                            const float v = __shfl_sync(0xFFFFFFFFu, e.bmax, L);
+                            if (bl < 0 || v < best) { best = v; bl = L; }
+                        }
+                        const float cand = __fadd_rn(run, best);
+                        if (!(__fmul_rn(cand, 1.00001f) < thr_val)) break;
+                        run = cand;
+                        ne_mask |= 1u << bl;
+                        rem &= ~(1u << bl);
+                    }
+                    const unsigned present = __ballot_sync(0xFFFFFFFFu, e.len > 0);
+                    const unsigned smask = present & ~ne_mask;
+                    if (ne_mask && smask == 0u) {  // only NE terms occur in this block
+                        n_skipped++;
+                        continue;
+                    }
+                    const int s_total = warp_sum(((smask >> lane) & 1u) ? e.len : 0);
+                    const int ne_total = warp_sum(((ne_mask >> lane) & 1u) ? e.len : 0);
+                    if (ne_mask && s_total <= kMsListCap && ne_total > 2 * s_total + 64) {
+                        // phase 1: bitmap of the documents any S term touches
+                        for (unsigned mm = smask; mm; mm &= mm - 1) {
+                            const int i = __ffs(mm) - 1;
+                            const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
+                            const long long s = shfl_ll(e.start, i);
+                            for (int j = lane; j < len; j += 32) {
+                                const int o = ld_nc_s32(a.indices + s + j) - doc_base;
+                                atomicOr(&cbm[o >> 5], 1u << (o & 31));
+                            }
+                        }
+                        __syncwarp();
+                        unsigned word = cbm[lane];
+                        cbm[lane] = 0u;
+                        const int cnt = __popc(word);
+                        int incl = cnt;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                            if (lane >= d) incl += y;
+                        }
+                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        int p = incl - cnt;
+                        while (word) {
+                            const int b = __ffs(word) - 1;
+                            word &= word - 1;
+                            clist[p++] = (uint16_t)(lane * 32 + b);
+                        }
+                        __syncwarp();
+                        // phase 2: all terms in query order
+                        for (int i = 0; i < m; i++) {
+                            const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
+                            if (!len) continue;
+                            if ((ne_mask >> i) & 1u) {
+                                const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
+                                const float *dv = a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base;
+                                for (int c = lane; c < total; c += 32) {
+                                    const int o = clist[c];
+                                    acc[o] = __fadd_rn(acc[o], ld_nc_f32(dv + o));
+                                }
+                            } else {
+                                const long long s = shfl_ll(e.start, i);
+                                scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                            }
+                            __syncwarp();
+                        }
+                        // epilogue over the candidates only (they are exactly the touched documents)
+                        unsigned int *mcnt = a.cand_cnt + q;
+                        unsigned long long *mrow = a.cand_key + (size_t)q * (size_t)a.cap;
+                        for (int c = lane; c < total; c += 32) {
+                            const int o = clist[c];
+                            const float v = acc[o];
+                            acc[o] = 0.f;
+                            emit_if_candidate(v, (uint32_t)(doc_base + o), thr_score, thr, mcnt, mrow, a.cap);
+                        }
+                        __syncwarp();
+                        n_ms++;
+                        continue;
+                    }
                 }
                 for (int i = 0; i < m; i++) {
                     const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
@@ -740,6 +872,7 @@ __global__ void __launch_bounds__(WARPS * 32, 6) block_kernel(const __grid_const
     if (lane == 0 && a.stats) {
         atomicAdd(&a.stats[0], n_units);
         atomicAdd(&a.stats[1], n_skipped);
+        atomicAdd(&a.stats[2], n_ms);
     }
 }
 
@@ -748,17 +881,23 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t 
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-    const size_t smem = (size_t)BK_WARPS * kBlockDocs * sizeof(float);
-    BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 6;
+    const bool ms = a.prune >= 2 && a.dense_vals != nullptr;
+    const size_t smem = (size_t)BK_WARPS * (ms ? warp_smem_bytes<true>() : warp_smem_bytes<false>());
+    int per_sm = ms ? 5 : 6;
     if (const char *e = getenv("BB25_CTAS_PER_SM")) {
         const int v = atoi(e);
-        if (v >= 1 && v <= 6) per_sm = v;
+        if (v >= 1 && v <= per_sm) per_sm = v;
     }
     long long grid = (long long)idx->sm_count * per_sm;
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
-    block_kernel<BK_WARPS><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+    if (ms) {
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        block_kernel<BK_WARPS, true><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+    } else {
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        block_kernel<BK_WARPS, false><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+    }
     BB25_LAUNCH_CHECK();
     return 0;
 }
@@ -940,7 +1079,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     unsigned int *d_nover = (unsigned int *)(ws + o_ctr + 8);
     int *d_err = (int *)(ws + o_ctr + 16);
     unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
-    unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [2]
+    unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [3]
     unsigned long long *d_keys = (unsigned long long *)(ws + o_key);
 
     const float *kth = nullptr;
@@ -1000,6 +1139,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.cand_key = d_keys;
     ba.cap = cap;
     ba.prune = idx->prune;
+    ba.dense_slot = idx->dense_slot;
+    ba.dense_vals = idx->dense_vals;
+    ba.dense_stride = idx->dense_stride;
     ba.work_counter = d_work;
     ba.stats = d_stats;
 
@@ -1088,12 +1230,13 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
             flip ^= 1;
         }
     }
-    BB25_CUDA(cudaMemcpyAsync(idx->pinned, d_ncand, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaMemcpyAsync(idx->pinned, d_ncand, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     BB25_CUDA(cudaStreamSynchronize(st));
     const unsigned long long *h_c = (const unsigned long long *)idx->pinned;
     idx->st_candidates = (int64_t)h_c[0];
     idx->st_units = (int64_t)h_c[1];
     idx->st_units_skipped = (int64_t)h_c[2];
+    idx->st_units_maxscore = (int64_t)h_c[3];
     for (int i = 0; i < idx->ev_used; i++) {
         float ms = 0.f;
         BB25_CUDA(cudaEventElapsedTime(&ms, idx->ev[2 * i], idx->ev[2 * i + 1]));
@@ -1202,17 +1345,19 @@ int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passe
     return 0;
 }
 
-int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped) {
+int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped,
+                              int64_t *units_maxscore) {
     if (!idx) { set_error("index is NULL"); return 1; }
     if (units) *units = idx->st_units;
     if (units_skipped) *units_skipped = idx->st_units_skipped;
+    if (units_maxscore) *units_maxscore = idx->st_units_maxscore;
     return 0;
 }
 
 int bb25_index_set_pruning(bb25_index *idx, int enable) {
     if (!idx) { set_error("index is NULL"); return 1; }
     std::lock_guard<std::mutex> lock(idx->mu);
-    idx->prune = enable ? 1 : 0;
+    idx->prune = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     return 0;
 }
 

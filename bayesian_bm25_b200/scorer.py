@@ -377,12 +377,13 @@ class BayesianBM25Scorer:
         ms, nl = C.c_double(), C.c_int64()
         _lib.check(_lib.lib().bb25_retrieve_timing(self._handle, C.byref(ms), C.byref(nl)))
         out["traverse_ms"], out["traverse_launches"] = ms.value, nl.value
-        u, sk = C.c_int64(), C.c_int64()
-        _lib.check(_lib.lib().bb25_retrieve_prune_stats(self._handle, C.byref(u), C.byref(sk)))
-        out["units"], out["units_skipped"] = u.value, sk.value
+        u, sk, ms_ = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().bb25_retrieve_prune_stats(self._handle, C.byref(u), C.byref(sk), C.byref(ms_)))
+        out["units"], out["units_skipped"], out["units_maxscore"] = u.value, sk.value, ms_.value
         return out
 
-    def set_pruning(self, enable: bool) -> None:
-        """Block-max pruning of (block, query) units in batch retrieve (exact either way)."""
+    def set_pruning(self, level: int) -> None:
+        """Dynamic pruning level of batch retrieve: 0 exhaustive, 1 block-max skip,
+        2 block-max skip + MaxScore (default).  Results are identical at every level."""
         self._require_index("set_pruning()")
-        _lib.check(_lib.lib().bb25_index_set_pruning(self._handle, int(bool(enable))))
+        _lib.check(_lib.lib().bb25_index_set_pruning(self._handle, int(level)))

@@ -231,39 +231,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 1)):
-        out = step()
-    barrier()
-
-    # ---- timed region: device-resident inputs, CUDA events, max over ranks ------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.lib().bb25_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    trav_ms, trav_launches, reruns, units, skipped = 0.0, 0, 0, 0, 0
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        out = step()
-        st = scorer.stats()
-        trav_ms += st["traverse_ms"]
-        trav_launches += st["traverse_launches"]
-        reruns += st["rerun_queries"]
-        units += st["units"]
-        skipped += st["units_skipped"]
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = int(_lib.lib().bb25_launch_count() - launches0)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, trav_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, trav_ms_max = float(t[0]), float(t[1])
-
-    # ---- end to end through the public host API (host buffers, H2D + D2H inside) -------
     def e2e_step():
+        """The call a user makes: host buffers in, host buffers out (H2D + D2H inside)."""
         if world == 1:
             return scorer.retrieve_ids(q_terms, q_off, args.k)
         hp = torch.empty(q_terms.size, dtype=torch.int32, pin_memory=True)
@@ -278,18 +247,56 @@ def main():
         torch.cuda.current_stream().synchronize()
         return h_ids.numpy(), h_pr.numpy()
 
-    for _ in range(3):  # lets torch's pinned-host allocator settle on reusable blocks
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e_out = e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
+    def measure(level: int, sample_clocks: bool):
+        """W warm-up + K timed steps at one pruning level: device-resident timing (CUDA
+        events, max over ranks) and the end-to-end host-API timing."""
+        scorer.set_pruning(level)
+        for _ in range(max(args.warmup, 1)):
+            out = step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        launches0 = _lib.lib().bb25_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = {"traverse_ms": 0.0, "traverse_launches": 0, "rerun_queries": 0, "units": 0, "units_skipped": 0,
+               "units_maxscore": 0}
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+            st = scorer.stats()
+            for key in acc:
+                acc[key] += st[key]
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = int(_lib.lib().bb25_launch_count() - launches0)
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        t = torch.tensor([ms, acc["traverse_ms"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for _ in range(3):  # lets torch's pinned-host allocator settle on reusable blocks
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return {"ms": float(t[0]), "trav_ms": float(t[1]), "launches": launches, "clocks": clocks,
+                "e2e_s": float(te[0]), "out": out, **{k_: v / args.steps for k_, v in acc.items() if k_ != "traverse_ms"}}
+
+    # headline: exhaustive traversal (every posting of every query term is visited, like the
+    # reference); then the same batch with the library's default dynamic pruning (exact)
+    ex = measure(0, sample_clocks=True)
+    pr = measure(2, sample_clocks=False)
+    same = all(bool(torch.equal(x, y)) for x, y in zip(ex["out"], pr["out"]))
+    out = ex["out"]
+    ms, trav_ms_max, launches, clocks, e2e_s = ex["ms"], ex["trav_ms"], ex["launches"], ex["clocks"], ex["e2e_s"]
+    trav_launches, reruns = ex["traverse_launches"] * args.steps, ex["rerun_queries"] * args.steps
     h2d = int(q_terms.nbytes + q_off.nbytes)
     d2h = int(args.queries * args.k * (8 + 8))
 
@@ -311,22 +318,30 @@ def main():
                 "cache": "inputs larger than L2 (CSC index %.2f GB per GPU, 126 MB L2)" % (nnz_full * 8 / world / 1e9),
                 "probabilities": "fp64 posterior fused on device", "index_build_s": round(t_build, 1),
                 "threshold_reruns_per_step": reruns / args.steps,
-                "kernel": os.environ.get("BB25_KERNEL", "block"),
-                "pruning": {"enabled": os.environ.get("BB25_PRUNE", "1") != "0", "block_docs": 1024,
-                            "units_per_step": units / args.steps, "units_skipped_per_step": skipped / args.steps},
+                "kernel": os.environ.get("BB25_KERNEL", "block"), "pruning_level": 0,
             },
             "clocks": clocks,
             "e2e": {"value": args.queries * args.steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
+            "pruned": {
+                "what": "same batch, library default: block-max skip + MaxScore (bb25_index_set_pruning level 2); "
+                        "results bit-identical to the exhaustive pass",
+                "value": args.queries * args.steps / (pr["ms"] / 1000.0), "unit": "queries/s",
+                "ms_per_step": pr["ms"] / args.steps, "kernel_ms_per_step": pr["trav_ms"] / args.steps,
+                "e2e_value": args.queries * args.steps / pr["e2e_s"], "results_identical": same,
+                "block_docs": 1024, "units_per_step": pr["units"], "units_skipped_per_step": pr["units_skipped"],
+                "units_maxscore_per_step": pr["units_maxscore"],
+            },
             "roofline": {
-                "bound": "hbm", "kernel": "bb25::tile_kernel (posting traversal + fused epilogue)",
+                "bound": "hbm", "kernel": "bb25::block_kernel (posting traversal + fused epilogue, exhaustive)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": ncu_traffic_per_launch(),
                 "algorithmic_bytes_per_step_per_gpu": alg_bytes_gpu,
                 "kernel_ms_per_step": trav_ms_max / args.steps, "kernel_launches_per_step": trav_launches / args.steps,
                 "note": "achieved = sum_q sum_t df(t)*8B (+k*20B) / summed traversal-kernel time (CUDA events in libbb25); "
-                        "all CTAs share a tile's index slice through L2, so DRAM traffic is far below the algorithmic bytes",
+                        "all warps share a block's index slice through L2, so DRAM traffic is far below the algorithmic "
+                        "bytes and the figure can exceed the HBM peak (DESIGN.md 4.1)",
             },
         }
         if host_csc is not None:

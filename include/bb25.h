@@ -125,13 +125,19 @@ int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const i
 int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passes,
                         int64_t *rerun_queries, int64_t *candidates);
 
-/* Block-max pruning (north star item 4).  The batch traversal works on 1024-document
- * blocks; a (block, query) unit whose block-max score bound (BlockMaxIndex semantics,
- * scorer.py:55-99, summed in query order) is below the query's current top-k threshold
- * cannot contribute and is skipped.  Results are identical with pruning on or off.
- * Default: on.  bb25_retrieve_prune_stats: units visited / skipped in the last batch. */
-int bb25_index_set_pruning(bb25_index *idx, int enable);
-int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped);
+/* Dynamic pruning (north star item 4).  The batch traversal works on 1024-document
+ * blocks with per-(block, term) maxima (BlockMaxIndex semantics, scorer.py:55-99).
+ *   level 0: exhaustive traversal;
+ *   level 1: a (block, query) unit whose summed block maxima stay below the query's
+ *            current top-k threshold cannot contribute and is skipped;
+ *   level 2 (default): additionally, in the remaining units, frequent terms whose block
+ *            maxima alone cannot reach the threshold are not traversed: their values
+ *            are looked up only for documents another query term touched (MaxScore).
+ * Results are bit-identical at every level.  bb25_retrieve_prune_stats: units visited /
+ * skipped / processed the MaxScore way in the last batch. */
+int bb25_index_set_pruning(bb25_index *idx, int level);
+int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped,
+                              int64_t *units_maxscore);
 
 /* Device time of the traversal kernel in the last bb25_retrieve_batch on this handle,
  * measured with CUDA events on the call's stream around every traversal launch

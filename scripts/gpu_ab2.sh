@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of traversal kernel families on the full bench (no CPU leg).
 mkdir -p gpurun_out
-CFGS=${AB2_CONFIGS:-tile:1:6 block:0:6 block:1:6 block:0:4 block:1:5}
+CFGS=${AB2_CONFIGS:-block:0:6 block:1:6 block:2:5}
 for cfg in $CFGS; do
   IFS=: read kern prune ctas <<< "$cfg"
   echo "== kernel $kern prune $prune ctas/SM $ctas"

@@ -191,10 +191,12 @@ def _queries_with_edge_cases(vocab, seed):
 
 
 @pytest.mark.parametrize("kernel,tile_docs,prune", [
-    ("block", 8192, 1), ("block", 8192, 0), ("tile", 8192, 1), ("tile", 16384, 1), ("tile", 32768, 1)])
+    ("block", 8192, 2), ("block", 8192, 1), ("block", 8192, 0), ("tile", 8192, 1), ("tile", 16384, 1),
+    ("tile", 32768, 1)])
 def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
-    """Both traversal kernels (warp-private blocks with and without block-max pruning,
-    CTA tiles at every tile size) must give the oracle's result bit for bit."""
+    """Both traversal kernels (warp-private blocks at every pruning level -- exhaustive,
+    block-max skip, block-max skip + MaxScore -- and CTA tiles at every tile size) must
+    give the oracle's result bit for bit."""
     pkg = _pkg()
     from bayesian_bm25_b200 import synthetic
     from oracle import coracle
@@ -222,6 +224,10 @@ def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
                 assert st["units_skipped"] == 0, st
             elif k == 1:
                 assert st["units_skipped"] > 0, st  # a top-1 threshold prunes most blocks
+            if prune == 2 and k <= 100:
+                assert st["units_maxscore"] > 0, st
+            if prune < 2:
+                assert st["units_maxscore"] == 0, st
     # dense surfaces
     for i in (0, 5, 7, 11, 13):
         q = flat[off[i]:off[i + 1]]
