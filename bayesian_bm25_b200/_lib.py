@@ -65,6 +65,9 @@ SIGNATURES = {
     "bb25_wand_upper_bound": (_i32, [_i32, _PP, _vp, _dbl, _i64, _vp, _vp]),
     "bb25_cosine_to_probability": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp]),
     "bb25_log_odds_conjunction": (_i32, [_i32, _vp, _i64, _i32, _vp, _dbl, _i32, _dbl, _i32, _dbl, _vp, _vp]),
+    "bb25_fuse_bm25_signal": (_i32, [_vp, _PP, _vp, _i32, _dbl, _i32, _dbl, _i32, _vp, _vp]),
+    "bb25_fuse_cosine_signal": (_i32, [_i32, _vp, _i64, _dbl, _i32, _dbl, _i32, _vp, _vp]),
+    "bb25_fuse_prob_signal": (_i32, [_i32, _vp, _i64, _dbl, _i32, _dbl, _i32, _vp, _vp]),
     "bb25_blockmax_dense": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "bb25_blockmax_csc": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
 }

@@ -61,6 +61,17 @@ static int run_ew(int device, EwArgs g, void *stream) {
     return 0;
 }
 
+// one cosine / probability signal of a log-odds conjunction, accumulated in place
+__global__ void __launch_bounds__(256) fuse_signal_kernel(const float *__restrict__ cosv,
+                                                          const double *__restrict__ probs, int64_t n,
+                                                          FuseSpec f, double *__restrict__ acc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double p = cosv ? clamp_prob((1.0 + (double)cosv[i]) / 2.0) : probs[i];  // fusion.py:43-45
+        acc[i] = fuse_step(acc[i], d_logit(p), f);
+    }
+}
+
 // fusion.py:119-169
 __device__ inline double d_gate(double x, int gating, double gb) {
     switch (gating) {
@@ -373,6 +384,30 @@ int bb25_log_odds_conjunction(int device, const double *probs, int64_t m, int n,
                                                                   has_max_logit, max_logit, out);
     BB25_LAUNCH_CHECK();
     return 0;
+}
+
+static int run_fuse_signal(int device, const float *cosv, const double *probs, int64_t n, double weight,
+                           int n_signals, double scale, int flags, double *acc, void *stream) {
+    if (n < 0 || !acc || n_signals < 1 || (flags & ~7) || (n > 0 && !cosv && !probs)) { set_error("bad fuse arguments"); return 1; }
+    if (n == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    FuseSpec f{weight, scale, n_signals, flags};
+    fuse_signal_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(cosv, probs, n, f, acc);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_fuse_cosine_signal(int device, const float *cosv, int64_t n, double weight, int n_signals, double scale,
+                            int flags, double *acc, void *stream) {
+    return run_fuse_signal(device, cosv, nullptr, n, weight, n_signals, scale, flags, acc, stream);
+}
+int bb25_fuse_prob_signal(int device, const double *probs, int64_t n, double weight, int n_signals, double scale,
+                          int flags, double *acc, void *stream) {
+    return run_fuse_signal(device, nullptr, probs, n, weight, n_signals, scale, flags, acc, stream);
 }
 
 int bb25_blockmax_dense(int device, const double *score_matrix, int64_t n_terms, int64_t n_docs,

@@ -98,6 +98,25 @@ __device__ inline double d_doc_probability(const bb25_params &p, float score, in
     return d_posterior(l, prior, p.has_base_rate, p.base_rate);
 }
 
+// ---- one signal of a log-odds conjunction, accumulated in place (fusion.py:243-280) ----
+// flags: 1 = first signal (ignore the previous contents), 2 = last signal (apply the
+// n**alpha scale and the sigmoid), 4 = unweighted mean branch (fusion.py:270-279)
+struct FuseSpec {
+    double weight;
+    double scale;  // n ** alpha, resolved by the caller
+    int n_signals;
+    int flags;
+};
+__device__ inline double fuse_step(double prev, double x, const FuseSpec &f) {
+    const double term = (f.flags & 4) ? x : f.weight * x;
+    const double acc = (f.flags & 1) ? (0.0 + term) : (prev + term);  // left-to-right, as NumPy sums the last axis
+    if (f.flags & 2) {
+        const double l = (f.flags & 4) ? (acc / (double)f.n_signals) * f.scale : f.scale * acc;
+        return d_sigmoid(l);
+    }
+    return acc;
+}
+
 // ---- candidate key: score desc, then local doc id asc ----------------------------
 // [63:33] fp32 score bits (scores are >= 0 so bit 31 is clear)
 // [32:4]  0x1FFFFFFF - local doc id   (n_docs <= 2^29 per index)

@@ -24,7 +24,7 @@ constexpr int QB = 8;      // queries per work item
 constexpr int MAXT = 128;  // (query, term) occurrences staged per metadata batch
 constexpr int kMaxK = 4096;
 
-enum { MODE_RETRIEVE = 0, MODE_SCORES = 1, MODE_PROBS = 2 };
+enum { MODE_RETRIEVE = 0, MODE_SCORES = 1, MODE_PROBS = 2, MODE_FUSED = 3 };
 
 struct TileArgs {
     const float *data;
@@ -50,6 +50,7 @@ struct TileArgs {
     double *out_probs;
     int64_t out_stride;
     bb25_params params;
+    FuseSpec fuse;  // MODE_FUSED only
     unsigned long long *work_counter;
 };
 
@@ -316,8 +317,17 @@ __global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE, VAR>()) tile_kernel(c
                             acc[w] = 0.f;
                             cnt[w] = 0;
                             if (d < a.n_docs) {
-                                if (MODE == MODE_SCORES) a.out_scores[d] = sc;
-                                else a.out_probs[d * a.out_stride] = d_doc_probability(a.params, sc, c, a.doc_len[d], a.avgdl);
+                                if (MODE == MODE_SCORES) {
+                                    a.out_scores[d] = sc;
+                                } else if (MODE == MODE_PROBS) {
+                                    a.out_probs[d * a.out_stride] = d_doc_probability(a.params, sc, c, a.doc_len[d], a.avgdl);
+                                } else {
+                                    // MODE_FUSED: this index is one signal of a log-odds conjunction
+                                    // (fusion.py:243-268): acc = [acc +] w * logit(clamp(p)); the last
+                                    // signal turns the sum into sigma(scale * acc)
+                                    const double p = d_doc_probability(a.params, sc, c, a.doc_len[d], a.avgdl);
+                                    a.out_probs[d] = fuse_step(a.out_probs[d], d_logit(p), a.fuse);
+                                }
                             }
                         }
                     }
@@ -977,9 +987,14 @@ static void base_args(const bb25_index *idx, TileArgs &a) {
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // dense single-query outputs (get_scores / get_probabilities)
+__global__ void fuse_const_kernel(double *acc, int64_t n, double p, FuseSpec f) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] = fuse_step(acc[i], d_logit(p), f);
+}
+
 static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const int32_t *q_terms_host,
                      int n_terms, float *out_scores, double *out_probs, int64_t out_stride,
-                     cudaStream_t st) {
+                     cudaStream_t st, const FuseSpec *fuse = nullptr) {
     if (!idx) { set_error("index is NULL"); return 1; }
     if (n_terms < 0 || (n_terms > 0 && !q_terms_host)) { set_error("bad query"); return 1; }
     DeviceGuard g(idx->device);
@@ -993,6 +1008,11 @@ static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const
     if (n_terms == 0) {
         if (mode == MODE_SCORES) {
             BB25_CUDA(cudaMemsetAsync(out_scores, 0, sizeof(float) * (size_t)idx->n_docs, st));
+        } else if (mode == MODE_FUSED) {
+            // no query term in the vocabulary: every document enters with probability 0 -> logit(1e-10)
+            fuse_const_kernel<<<(unsigned)((idx->n_docs + 255) / 256), 256, 0, st>>>(out_probs, idx->n_docs,
+                                                                                    0.0, *fuse);
+            BB25_LAUNCH_CHECK();
         } else {
             fill_strided_f64_kernel<<<(unsigned)((idx->n_docs + 255) / 256), 256, 0, st>>>(out_probs, idx->n_docs, out_stride, 0.0);
             BB25_LAUNCH_CHECK();
@@ -1035,7 +1055,9 @@ static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const
     a.out_stride = out_stride;
     if (params) a.params = *params;
     a.work_counter = (unsigned long long *)(ws + o_ctr);
+    if (fuse) a.fuse = *fuse;
     if (mode == MODE_SCORES) return launch_tile<MODE_SCORES>(idx, a, st);
+    if (mode == MODE_FUSED) return launch_tile<MODE_FUSED>(idx, a, st);
     return launch_tile<MODE_PROBS>(idx, a, st);
 }
 
@@ -1263,6 +1285,14 @@ int bb25_get_probabilities(bb25_index *idx, const bb25_params *params, const int
     if (!out_probs || out_stride < 1) { set_error("bad output arguments"); return 1; }
     if (check_params(params)) return 1;
     return run_dense(idx, MODE_PROBS, params, q_terms, n_terms, nullptr, out_probs, out_stride, (cudaStream_t)stream);
+}
+
+int bb25_fuse_bm25_signal(bb25_index *idx, const bb25_params *params, const int32_t *q_terms, int n_terms,
+                          double weight, int n_signals, double scale, int flags, double *acc, void *stream) {
+    if (!acc || n_signals < 1 || (flags & ~7)) { set_error("bad fuse arguments"); return 1; }
+    if (check_params(params)) return 1;
+    FuseSpec f{weight, scale, n_signals, flags};
+    return run_dense(idx, MODE_FUSED, params, q_terms, n_terms, nullptr, acc, 1, (cudaStream_t)stream, &f);
 }
 
 int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,

@@ -1,9 +1,9 @@
 """MultiFieldScorer on the B200 path (reference: ``bayesian_bm25/multi_field.py``).
 
-One BayesianBM25Scorer (device index) per field; per-field dense probabilities
-are written column-stacked into one device buffer, fused by the
-log_odds_conjunction kernel and ranked by the dense top-k kernel -- nothing
-leaves the device until the final (k,) result.
+One BayesianBM25Scorer (device index) per field.  The weighted log-odds conjunction
+is fused into each field's traversal pass (bb25_fuse_bm25_signal), the fused vector is
+ranked by the dense top-k kernel -- nothing leaves the device until the final (k,)
+result.
 """
 from __future__ import annotations
 
@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .fusion import _resolve_alpha, log_odds_conjunction_device
+from .fusion import _resolve_alpha
 from .scorer import BayesianBM25Scorer
 
 MAX_DEVICE_TOPK = 8192
@@ -93,14 +93,19 @@ class MultiFieldScorer:
         self._num_docs += len(new_documents)
 
     def _fused_device(self, per_field_terms) -> torch.Tensor:
+        """Fused probability of every document, on the device.  One pass per field: the
+        field's traversal kernel turns its BM25 accumulators into the posterior, takes
+        the logit and adds w_f * logit into ONE shared accumulator; the last field
+        applies n**alpha and the sigmoid (multi_field.py:158-174 without the [N, F]
+        matrix)."""
         nf = len(self._fields)
         first = self._scorers[self._fields[0]]
-        buf = torch.empty((self._num_docs, nf), dtype=torch.float64, device=first._device)
+        acc = torch.empty(self._num_docs, dtype=torch.float64, device=first._device)
+        scale = float(nf ** _resolve_alpha(self._alpha, default=0.5))
         for j, f in enumerate(self._fields):
-            # column j of the row-major [N, F] buffer: element d at buf[d, j]
-            self._scorers[f].probabilities_device(per_field_terms[j], out=buf[:, j], stride=nf)
-        w = np.array([self._field_weights[f] for f in self._fields], dtype=np.float64)
-        return log_odds_conjunction_device(buf, alpha=_resolve_alpha(self._alpha, default=0.5), weights=w)
+            flags = (1 if j == 0 else 0) | (2 if j == nf - 1 else 0)
+            self._scorers[f].fuse_signal_device(per_field_terms[j], self._field_weights[f], nf, scale, flags, acc)
+        return acc
 
     def get_probabilities(self, query_tokens: list[str]) -> np.ndarray:
         """Fused probability of every document (multi_field.py:141-174)."""

@@ -280,6 +280,20 @@ class BayesianBM25Scorer:
                                                      out.data_ptr(), stride, _lib.stream_ptr()))
         return out
 
+    def fuse_signal_device(self, term_ids, weight: float, n_signals: int, scale: float, flags: int,
+                           acc: torch.Tensor) -> torch.Tensor:
+        """This index as ONE signal of a log-odds conjunction, fused into the traversal
+        pass: acc[d] = [acc[d] +] weight * logit(clamp(P(d | query))) and, on the last
+        signal (flags & 2), sigmoid(scale * acc[d]).  flags & 1 = first signal,
+        flags & 4 = unweighted-mean branch (see include/bb25.h)."""
+        self._require_index("fuse_signal_device()")
+        q = np.ascontiguousarray(term_ids, dtype=np.int32)
+        p = self._params()
+        _lib.check(_lib.lib().bb25_fuse_bm25_signal(self._handle, C.byref(p), q.ctypes.data, q.size, float(weight),
+                                                    int(n_signals), float(scale), int(flags), acc.data_ptr(),
+                                                    _lib.stream_ptr()))
+        return acc
+
     def get_probabilities(self, query_tokens: list[str]) -> np.ndarray:
         """Probabilities for ALL documents, 0.0 where the score is <= 0 (scorer.py:564-590)."""
         if self._transform is None:

@@ -146,7 +146,7 @@ def run_reference(args):
     q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, QUERY_SEED)
     from oracle import coracle
     cores = coracle.max_threads()
-    sample = min(args.queries, max(128, 8 * cores))
+    sample = min(args.queries, max(256, 24 * cores))
     for _ in range(args.warmup):
         cpu_baseline(host, q_terms, q_off, args.k, min(sample, cores))
     times = []
@@ -347,7 +347,7 @@ def main():
         if host_csc is not None:
             from oracle import coracle
             cores = coracle.max_threads()
-            sample = args.cpu_sample or min(args.queries, max(128, 8 * cores))
+            sample = args.cpu_sample or min(args.queries, max(256, 24 * cores))
             v, used, dt = cpu_baseline(host_csc, q_terms, q_off, args.k, sample)
             line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": used, "kind": "port",
                                     "sample": f"first {sample} queries of the batch, oracle/bb25_oracle.c, {dt:.1f} s wall"}

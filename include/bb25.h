@@ -188,6 +188,28 @@ int bb25_log_odds_conjunction(int device, const double *probs, int64_t m, int n,
                               double gating_beta, int has_max_logit, double max_logit,
                               double *out, void *stream);
 
+/*
+ * Fused form of the same conjunction for dense, per-document signals (ungated, no
+ * max_logit): one accumulator acc[N] (dev fp64) is updated in place, one call per
+ * signal in signal order, so neither the per-signal probability vectors nor the
+ * column-stacked [N, n] matrix of multi_field.py:158-161 are ever materialised:
+ *     acc = [acc +] w * logit(clamp(p_signal))            flags & 1: first signal
+ *     acc = sigmoid(scale * acc)  (or sigmoid(acc / n * scale) when flags & 4) on the
+ *                                                         flags & 2: last signal
+ * bb25_fuse_bm25_signal evaluates the signal inside the traversal kernel's epilogue
+ * (BM25 accumulate -> posterior -> logit -> weighted add in one pass over the index);
+ * p = 0.0 for documents the query does not match (scorer.py:618, fusion.py:243).
+ * bb25_fuse_cosine_signal takes fp32 cosine similarities (cosine_to_probability,
+ * fusion.py:43-45), bb25_fuse_prob_signal ready-made fp64 probabilities.
+ */
+int bb25_fuse_bm25_signal(bb25_index *idx, const bb25_params *params, const int32_t *q_terms /*host*/,
+                          int n_terms, double weight, int n_signals, double scale, int flags,
+                          double *acc /*dev [N]*/, void *stream);
+int bb25_fuse_cosine_signal(int device, const float *cosine /*dev*/, int64_t n, double weight, int n_signals,
+                            double scale, int flags, double *acc, void *stream);
+int bb25_fuse_prob_signal(int device, const double *probs /*dev*/, int64_t n, double weight, int n_signals,
+                          double scale, int flags, double *acc, void *stream);
+
 /* ---- a12: BlockMaxIndex ---------------------------------------------------- */
 
 /* BlockMaxIndex.build (scorer.py:55-81) on a dense [n_terms][n_docs] fp64

@@ -363,6 +363,39 @@ def test_multifield_vs_reference(golden_mf):
     np.testing.assert_allclose(fused[nzm], alone[nzm], atol=1e-6)
 
 
+def test_hybrid_fusion_vs_oracle():
+    """BASELINE configs[3] semantics: BM25 posterior + cosine_to_probability through weighted /
+    unweighted log_odds_conjunction, fused on the device, against the oracle's composition of
+    the same reference formulas; top-100 with (value desc, id asc) ties."""
+    pkg = _pkg()
+    from bayesian_bm25_b200 import hybrid, synthetic
+    from oracle import coracle
+    n_docs, vocab = 60_000, 2000
+    csc = synthetic.zipf_csc(n_docs, vocab, 40.0, seed=31, device=torch.device("cuda:0"))
+    host = _host(csc)
+    sc = pkg.BayesianBM25Scorer(alpha=1.8, beta=0.6, base_rate=0.02)
+    sc.index_from_csc(csc)
+    params = coracle.make_params(1.8, 0.6, 0.02)
+    rng = np.random.default_rng(44)
+    for q in ([3, 17, 250], [0, 1], [], [1999, 5, 5]):
+        cos = np.clip(rng.normal(0.2, 0.15, n_docs), -1, 1).astype(np.float32)
+        p_b = coracle.get_probabilities(host, params, q)
+        p_v = coracle.cosine_to_probability(cos.astype(np.float64))
+        stacked = np.stack([p_b, p_v], axis=-1)
+        for weights, alpha in (((0.6, 0.4), None), ((0.6, 0.4), 0.5), (None, None), (None, "auto"), ((0.5, 0.5), 1.0)):
+            want = coracle.log_odds_conjunction(stacked, alpha=alpha, weights=weights)
+            got = hybrid.hybrid_probabilities_device(sc, q, torch.from_numpy(cos).cuda(), weights, alpha).cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-18)
+            # the composed (unfused) public functions give the same numbers
+            comp = pkg.log_odds_conjunction(np.stack([sc.probabilities_device(q).cpu().numpy(),
+                                                      pkg.cosine_to_probability(cos)], axis=-1), alpha=alpha, weights=weights)
+            np.testing.assert_array_equal(got, comp)
+            ids, vals = hybrid.hybrid_retrieve(sc, q, torch.from_numpy(cos).cuda(), k=100, weights=weights, alpha=alpha)
+            w_ids, w_vals = coracle.topk_f64(got, 100)
+            np.testing.assert_array_equal(ids, w_ids)
+            np.testing.assert_array_equal(vals, w_vals)
+
+
 def test_blockmax_vs_reference(golden_mf):
     pkg = _pkg()
     from bayesian_bm25_b200 import synthetic
