@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) build_block_table_kernel(const float *__r
         }
     }
 }
-// dense_vals[slot][doc] = value of the slot's term in doc (0.0f where absent)
+// dense_vals[slot][doc] = value of the slot's term in doc (rows pre-filled with -0.0f = absent)
 __global__ void __launch_bounds__(256) build_dense_rows_kernel(const float *__restrict__ data,
                                                                const int32_t *__restrict__ indices,
                                                                const int64_t *__restrict__ indptr,
@@ -99,6 +99,10 @@ __global__ void __launch_bounds__(256) build_dense_rows_kernel(const float *__re
     float *row = dense + (int64_t)blockIdx.y * stride;
     for (int64_t j = s + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (int64_t)gridDim.x * blockDim.x)
         row[indices[j]] = data[j];
+}
+__global__ void fill_u32_kernel(unsigned int *p, size_t n, unsigned int v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 __global__ void init_block_table_kernel(uint2 *tab, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -377,7 +381,10 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
         if (idx->n_dense > 0) {
             const size_t nb = (size_t)idx->n_dense * (size_t)idx->dense_stride * sizeof(float);
             TRY(cudaMalloc(&idx->dense_vals, nb));
-            TRY(cudaMemset(idx->dense_vals, 0, nb));
+            // absent documents hold -0.0f: x + (-0.0f) == x exactly, and the sign bit keeps
+            // "absent" distinguishable from a posting whose value is +0.0f
+            fill_u32_kernel<<<(unsigned)((nb / 4 + 255) / 256), 256>>>(reinterpret_cast<unsigned int *>(idx->dense_vals), nb / 4, 0x80000000u);
+            count_launch();
             idx->device_bytes += nb;
             int32_t *d_terms = nullptr;
             TRY(cudaMalloc(&d_terms, h_terms.size() * sizeof(int32_t)));

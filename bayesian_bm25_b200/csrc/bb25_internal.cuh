@@ -154,7 +154,7 @@ struct bb25_index {
     int n_blocks = 0;
     int prune = 2;  // 0 exhaustive, 1 skip (block, query) units under the block-max bound, 2 + MaxScore units
     // dense value rows for the most frequent terms (df >= n_docs/8, at most kMaxDenseTerms):
-    // dense_vals[slot][doc] = posting value or 0.0f; O(1) lookup of a head term's
+    // dense_vals[slot][doc] = posting value, or -0.0f where absent; O(1) lookup of a head term's
     // contribution to one document, used by the MaxScore path of the block kernel
     int32_t *dense_slot = nullptr;  // [n_vocab] slot or -1
     float *dense_vals = nullptr;    // [n_dense][dense_stride]

@@ -400,8 +400,11 @@ struct SelectArgs {
     int tf_search;
     const int32_t *indices;
     const int64_t *indptr;
-    const uint32_t *tile_off;
-    int n_tiles, tile_docs;
+    const uint2 *blk_tab;
+    int64_t n_vocab;
+    const int32_t *dense_slot;
+    const float *dense_vals;
+    int64_t dense_stride;
     const int32_t *q_terms;
     const uint8_t *q_nocount;
     const int64_t *q_off;
@@ -409,18 +412,26 @@ struct SelectArgs {
 };
 
 // scorer.py:592-601 for one (query, document): number of distinct query terms whose
-// posting list contains the document
+// posting list contains the document.  Head terms answer from their dense value row
+// (absent documents hold -0.0f, so presence is one load even when the value is +0.0f);
+// other terms by binary search inside the document's 1024-doc block slice.
 __device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t doc) {
     const long long t0 = a.q_off[q] - a.term_base, t1 = a.q_off[q + 1] - a.term_base;
-    const int tile = (int)(doc / (uint32_t)a.tile_docs);
+    const uint2 *row = a.blk_tab + (size_t)(doc / (uint32_t)kBlockDocs) * (size_t)a.n_vocab;
     int c = 0;
     for (long long i = t0; i < t1; i++) {
         if (a.q_nocount[i]) continue;  // duplicate occurrence of an earlier term
         const int t = a.q_terms[i];
-        const uint32_t *to = a.tile_off + (size_t)t * (size_t)(a.n_tiles + 1) + tile;
-        const long long base = a.indptr[t];
-        long long lo = base + to[0];
-        const long long end = base + to[1];
+        const int slot = a.dense_slot[t];
+        if (slot >= 0) {
+            c += (__float_as_uint(a.dense_vals[(size_t)slot * (size_t)a.dense_stride + doc]) != 0x80000000u);
+            continue;
+        }
+        const uint2 ent = row[t];
+        const int len = (int)(ent.y & kBlkLenMask);
+        if (len == 0) continue;
+        long long lo = a.indptr[t] + (long long)ent.x;
+        const long long end = lo + len;
         long long hi = end;
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
@@ -1187,9 +1198,11 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.tf_search = (blockk || (kernel_variant() & 2)) ? 1 : 0;  // keys carry no tf in those kernels
     sa.indices = idx->indices;
     sa.indptr = idx->indptr;
-    sa.tile_off = idx->tile_off;
-    sa.n_tiles = idx->n_tiles;
-    sa.tile_docs = idx->tile_docs;
+    sa.blk_tab = idx->blk_tab;
+    sa.n_vocab = idx->n_vocab;
+    sa.dense_slot = idx->dense_slot;
+    sa.dense_vals = idx->dense_vals;
+    sa.dense_stride = idx->dense_stride;
     sa.q_terms = d_terms;
     sa.q_nocount = d_nc;
     sa.q_off = q_off;

@@ -51,13 +51,31 @@ def merge_topk_device(ids: torch.Tensor, scores: torch.Tensor, probs: torch.Tens
 class ShardedRetriever:
     """Wraps a rank-local BayesianBM25Scorer (indexed on this rank's shard)."""
 
-    def __init__(self, scorer, group=None):
+    def __init__(self, scorer, group=None, profile: bool = False):
         self.scorer = scorer
         self.group = group
+        self.profile = profile
+        self.timing = {"local_ms": 0.0, "gather_ms": 0.0, "merge_ms": 0.0, "calls": 0}
 
     def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
+        sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (self.profile and sharded) else None
+        if ev:
+            ev[0].record()
         ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k)
-        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
-            return merge_topk_device(g_ids, g_sc, g_pr)
-        return ids, sc, pr
+        if not sharded:
+            return ids, sc, pr
+        if ev:
+            ev[1].record()
+        g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
+        if ev:
+            ev[2].record()
+        out = merge_topk_device(g_ids, g_sc, g_pr)
+        if ev:
+            ev[3].record()
+            ev[3].synchronize()
+            self.timing["local_ms"] += ev[0].elapsed_time(ev[1])
+            self.timing["gather_ms"] += ev[1].elapsed_time(ev[2])
+            self.timing["merge_ms"] += ev[2].elapsed_time(ev[3])
+            self.timing["calls"] += 1
+        return out

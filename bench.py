@@ -217,7 +217,7 @@ def main():
     scorer.index_from_csc(csc)
     del csc
     torch.cuda.empty_cache()
-    retr = sharded.ShardedRetriever(scorer)
+    retr = sharded.ShardedRetriever(scorer, profile=world > 1)
     q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, QUERY_SEED)
     d_terms = torch.from_numpy(q_terms).to(dev)
     d_off = torch.from_numpy(q_off).to(dev)
@@ -292,6 +292,7 @@ def main():
     # headline: exhaustive traversal (every posting of every query term is visited, like the
     # reference); then the same batch with the library's default dynamic pruning (exact)
     ex = measure(0, sample_clocks=True)
+    shard_timing = dict(retr.timing)
     pr = measure(2, sample_clocks=False)
     same = all(bool(torch.equal(x, y)) for x, y in zip(ex["out"], pr["out"]))
     out = ex["out"]
@@ -321,6 +322,8 @@ def main():
                 "kernel": os.environ.get("BB25_KERNEL", "block"), "pruning_level": 0,
             },
             "clocks": clocks,
+            "sharded_breakdown_ms_per_call": ({k_: v / max(1, shard_timing["calls"]) for k_, v in shard_timing.items()
+                                               if k_ != "calls"} if world > 1 else None),
             "e2e": {"value": args.queries * args.steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
