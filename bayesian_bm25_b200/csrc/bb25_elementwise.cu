@@ -139,53 +139,70 @@ __global__ void __launch_bounds__(256) blockmax_csc_kernel(const float *__restri
 }
 
 // ---- K7: merge S sorted [Q,k] lists --------------------------------------------------
+// One CTA per query: the S*k (score, global id) keys are loaded into shared memory, the
+// k-th largest is found by radix select, the k winners are compacted with their source
+// positions and sorted (k elements instead of S*k).
 template <int NT>
 __global__ void __launch_bounds__(NT) merge_kernel(const int64_t *__restrict__ ids,
                                                    const float *__restrict__ scores,
                                                    const double *__restrict__ probs, int S, int64_t Q,
-                                                   int k, int P, int64_t *__restrict__ out_ids,
+                                                   int k, int kpad, int64_t *__restrict__ out_ids,
                                                    float *__restrict__ out_scores,
                                                    double *__restrict__ out_probs) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int n = S * k;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
-    unsigned int *src = reinterpret_cast<unsigned int *>(smem + (size_t)P * 8);
+    unsigned long long *top = keys + n;
+    unsigned int *tsrc = reinterpret_cast<unsigned int *>(top + kpad);
+    unsigned int *hist = tsrc + kpad;
+    unsigned int *st = hist + 256;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n = S * k;
-    for (int i = tid; i < P; i += NT) {
-        if (i < n) {
-            const int s = i / k, r = i % k;
-            const int64_t o = ((int64_t)s * Q + q) * k + r;
-            // (score desc, global id asc); ids < 2^32
-            keys[i] = ((unsigned long long)__float_as_uint(scores[o]) << 32) |
-                      (unsigned long long)(0xFFFFFFFFu - (uint32_t)ids[o]);
-            src[i] = (unsigned int)i;
-        } else {
-            keys[i] = 0ull;
-            src[i] = 0xFFFFFFFFu;
+    for (int i = tid; i < n; i += NT) {
+        const int s = i / k, r = i % k;
+        const int64_t o = ((int64_t)s * Q + q) * k + r;
+        // (score desc, global id asc); ids < 2^32
+        keys[i] = ((unsigned long long)__float_as_uint(scores[o]) << 32) |
+                  (unsigned long long)(0xFFFFFFFFu - (uint32_t)ids[o]);
+    }
+    for (int i = tid; i < kpad; i += NT) {
+        top[i] = 0ull;
+        tsrc[i] = 0xFFFFFFFFu;
+    }
+    if (tid == 0) st[2] = 0u;
+    __syncthreads();
+    const unsigned long long kth = block_kth_largest<NT>(keys, n, k, hist, st, tid);
+    for (int i = tid; i < n; i += NT) {
+        const unsigned long long key = keys[i];
+        if (key >= kth) {
+            const unsigned int pos = atomicAdd(&st[2], 1u);
+            if (pos < (unsigned)kpad) {
+                top[pos] = key;
+                tsrc[pos] = (unsigned int)i;
+            }
         }
     }
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1)
+    for (int size = 2; size <= kpad; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (P >> 1); t += NT) {
+            for (int t = tid; t < (kpad >> 1); t += NT) {
                 const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
                 const bool desc = (lo & size) == 0;
-                const unsigned long long x = keys[lo], y = keys[hi];
-                // padding keys (src == ~0) must lose against real zero-score, id = 2^32-1 ... keys
-                const bool less = x < y || (x == y && src[lo] > src[hi]);
+                const unsigned long long x = top[lo], y = top[hi];
+                // padding (src == ~0) loses against any real entry with an equal key
+                const bool less = x < y || (x == y && tsrc[lo] > tsrc[hi]);
                 if (less == desc) {
-                    keys[lo] = y;
-                    keys[hi] = x;
-                    const unsigned int sx = src[lo];
-                    src[lo] = src[hi];
-                    src[hi] = sx;
+                    top[lo] = y;
+                    top[hi] = x;
+                    const unsigned int sx = tsrc[lo];
+                    tsrc[lo] = tsrc[hi];
+                    tsrc[hi] = sx;
                 }
             }
             __syncthreads();
         }
     for (int r = tid; r < k; r += NT) {
-        const unsigned int i = src[r];
+        const unsigned int i = tsrc[r];
         const int s = i / k, rr = i % k;
         const int64_t o = ((int64_t)s * Q + q) * k + rr;
         out_ids[q * k + r] = ids[o];
@@ -453,12 +470,12 @@ int bb25_merge_topk(int device, const int64_t *ids, const float *scores, const d
     if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
     DeviceGuard dg(device);
     if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
-    int P = 2;
-    while (P < n_shards * k) P <<= 1;
-    const size_t smem = (size_t)P * 12;
-    BB25_CUDA(cudaFuncSetAttribute(merge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
-    merge_kernel<512><<<(unsigned)n_queries, 512, smem, (cudaStream_t)stream>>>(ids, scores, probs, n_shards, n_queries, k, P,
-                                                                               out_ids, out_scores, out_probs);
+    int kpad = 2;
+    while (kpad < k) kpad <<= 1;
+    const size_t smem = (size_t)n_shards * k * 8 + (size_t)kpad * 12 + 260 * 4;
+    BB25_CUDA(cudaFuncSetAttribute(merge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<512><<<(unsigned)n_queries, 512, smem, (cudaStream_t)stream>>>(ids, scores, probs, n_shards, n_queries, k,
+                                                                               kpad, out_ids, out_scores, out_probs);
     BB25_LAUNCH_CHECK();
     return 0;
 }

@@ -133,6 +133,62 @@ __host__ __device__ inline uint32_t key_local_id(unsigned long long k) {
 }
 __host__ __device__ inline uint32_t key_tf(unsigned long long k) { return (uint32_t)(k & 15ull); }
 
+// k-th largest of n distinct 64-bit keys held in shared memory (n >= k >= 1): MSB-first
+// radix select, 8 passes of 8 bits, one 256-bin histogram per pass.  All threads of the
+// block must call it; hist = 256 words, st = 2 words of shared scratch.
+template <int NT>
+__device__ unsigned long long block_kth_largest(const unsigned long long *keys, int n, int k, unsigned int *hist,
+                                                unsigned int *st, int tid) {
+    unsigned long long prefix = 0ull, mask = 0ull;
+    unsigned int rem = (unsigned int)k;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int i = tid; i < 256; i += NT) hist[i] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const unsigned long long key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned int)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane L owns bins 255-8L .. 248-8L (descending); scan the lane sums, then the
+            // owning lane walks its 8 bins
+            unsigned int loc[8];
+            unsigned int sum = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                loc[j] = hist[255 - (8 * tid + j)];
+                sum += loc[j];
+            }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (tid >= d) incl += y;
+            }
+            const unsigned int excl = incl - sum;
+            if (excl < rem && rem <= incl) {
+                unsigned int c = excl;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (c + loc[j] >= rem) {
+                        st[0] = (unsigned int)(255 - (8 * tid + j));
+                        st[1] = rem - c;
+                        break;
+                    }
+                    c += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)st[0] << shift;
+        mask |= 255ull << shift;
+        rem = st[1];
+        // the next pass (or the caller) synchronises before st / hist are written again
+    }
+    return prefix;
+}
+
 }  // namespace bb25
 
 struct bb25_index {

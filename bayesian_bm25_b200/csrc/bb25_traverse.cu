@@ -462,28 +462,41 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int 
     }
 }
 
+// Shared-memory plan of select_kernel: keys u64[cap] | top u64[kpad] | hist u32[256] |
+// st u32[4] | flag u8[kpad]   (kpad = k rounded up to a power of two)
 template <int NT>
 __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ SelectArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int k = a.k;
+    int kpad = 2;
+    while (kpad < k) kpad <<= 1;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
-    uint8_t *flag = smem + (size_t)a.cap * 8;
+    unsigned long long *top = keys + a.cap;
+    unsigned int *hist = reinterpret_cast<unsigned int *>(top + kpad);
+    unsigned int *st = hist + 256;
+    uint8_t *flag = reinterpret_cast<uint8_t *>(st + 4);
     const int tid = threadIdx.x;
     const int q = a.q_list ? a.q_list[blockIdx.x] : (int)blockIdx.x;
     const unsigned int n_raw = a.cand_cnt[q];
     const int n = (int)min(n_raw, (unsigned)a.cap);
     unsigned long long *row = a.cand_key + (size_t)q * (size_t)a.cap;
-    int P = 2;
-    while (P < n) P <<= 1;
-    for (int i = tid; i < P; i += NT) keys[i] = i < n ? row[i] : 0ull;
-    __syncthreads();
-    bitonic_sort_desc<NT>(keys, P, tid);
-    const int k = a.k;
+    const bool overflow = n_raw > (unsigned)a.cap;
 
-    if (n_raw > (unsigned)a.cap) {
+    if (!overflow && !a.final_pass && n <= k) {
+        // nothing to drop and no tighter bound to learn yet
+        if (tid == 0) a.n_prev[q] = (unsigned int)n;
+        return;
+    }
+    for (int i = tid; i < n; i += NT) keys[i] = row[i];
+    __syncthreads();
+    unsigned long long kth = 0ull;
+    if (n >= k) kth = block_kth_largest<NT>(keys, n, k, hist, st, tid);
+
+    if (overflow) {
         // more candidates than the row holds: the k-th best of the stored ones is a
         // valid, strictly tighter bound; redo this tile group for this query
         if (tid == 0) {
-            a.thr[q] = keys[k - 1] & ~15ull;
+            a.thr[q] = kth & ~15ull;
             a.cand_cnt[q] = a.n_prev[q];
             const unsigned int pos = atomicAdd(a.n_over, 1u);
             a.over_list[pos] = q;
@@ -491,22 +504,37 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         return;
     }
     if (!a.final_pass) {
-        const int keep = min(n, k);
-        for (int i = tid; i < keep; i += NT) row[i] = keys[i];
+        // keep the best k (order irrelevant), raise the threshold to the k-th key
+        if (tid == 0) st[2] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const unsigned long long key = keys[i];
+            if (key >= kth) row[atomicAdd(&st[2], 1u)] = key;
+        }
         if (tid == 0) {
-            a.cand_cnt[q] = keep;
-            a.n_prev[q] = keep;
-            if (n >= k) {
-                const unsigned long long t = keys[k - 1] & ~15ull;
-                if (t > a.thr[q]) a.thr[q] = t;
-            }
+            a.cand_cnt[q] = (unsigned int)k;
+            a.n_prev[q] = (unsigned int)k;
+            const unsigned long long t = kth & ~15ull;
+            if (t > a.thr[q]) a.thr[q] = t;
         }
         return;
     }
+    // final pass: the best min(n, k) keys, sorted
     const int n_pos = min(n, k);
+    if (tid == 0) st[2] = 0u;
+    for (int i = tid; i < kpad; i += NT) top[i] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+        const unsigned long long key = keys[i];
+        if (key >= kth) top[atomicAdd(&st[2], 1u)] = key;
+    }
+    __syncthreads();
+    int P = 2;
+    while (P < n_pos) P <<= 1;
+    bitonic_sort_desc<NT>(top, P, tid);
     if (tid == 0 && a.n_cand_total) atomicAdd(a.n_cand_total, (unsigned long long)n);
     for (int r = tid; r < n_pos; r += NT) {
-        const unsigned long long key = keys[r];
+        const unsigned long long key = top[r];
         const uint32_t id = key_local_id(key);
         const float sc = __uint_as_float(key_score_bits(key));
         const size_t o = (size_t)q * (size_t)k + r;
@@ -522,7 +550,7 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         for (int i = tid; i < k; i += NT) flag[i] = 0;
         __syncthreads();
         for (int r = tid; r < n_pos; r += NT) {
-            const uint32_t id = key_local_id(keys[r]);
+            const uint32_t id = key_local_id(top[r]);
             if (id < (uint32_t)k) flag[id] = 1;
         }
         __syncthreads();
@@ -544,7 +572,6 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         }
     }
 }
-
 
 // =================================================================================
 // Warp-private traversal (retrieve mode).  A BLOCK = 1024 consecutive documents whose
@@ -1208,8 +1235,10 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.q_off = q_off;
     sa.term_base = term_base;
 
-    const size_t sel_smem = (size_t)cap * 9;
-    BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 9));
+    int kpad = 2;
+    while (kpad < k) kpad <<= 1;
+    const size_t sel_smem = (size_t)cap * 8 + (size_t)kpad * 9 + 260 * 4;
+    BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     unsigned int *h_flags = (unsigned int *)idx->pinned;  // [0] n_over, [1] err
 
     for (int gi = 0; gi < ng; gi++) {
