@@ -240,6 +240,9 @@ def main():
         ho = torch.empty(q_off.size, dtype=torch.int64, pin_memory=True)
         ho.numpy()[:] = q_off
         ids, sc, pr = retr.retrieve_ids_device(hp.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), args.k)
+        if rank != 0:  # the merged result is identical on every rank; the caller lives on rank 0
+            torch.cuda.current_stream().synchronize()
+            return None
         h_ids = torch.empty(ids.shape, dtype=ids.dtype, pin_memory=True)
         h_pr = torch.empty(pr.shape, dtype=pr.dtype, pin_memory=True)
         h_ids.copy_(ids, non_blocking=True)
