@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Secondary BASELINE.json configurations (not the driver's bench line):
+
+  config 4  hybrid fusion: BM25 posterior + cosine_to_probability through weighted
+            log_odds_conjunction, top-100, on the config-2 corpus (8.8 M docs);
+  config 5  MultiFieldScorer (title + body) top-10 on a large two-field corpus
+            (default 50 M docs; --mf-docs to change).
+
+Each prints one JSON line with device-timed queries/s, the per-query kernel count and
+a parity spot check against the CPU oracle.  Run on a B200:
+    python scripts/bench_configs.py --config 4
+    python scripts/bench_configs.py --config 5 --mf-docs 50000000
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bayesian_bm25_b200 import BayesianBM25Scorer, MultiFieldScorer, _lib, hybrid, synthetic  # noqa: E402
+
+VOCAB = 30_000
+ALPHA, BETA, BASE_RATE = 2.0, 0.2, 0.045
+
+
+def _host(csc):
+    return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in csc.items()}
+
+
+def _time(fn, n_iter):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_iter):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def config4(args):
+    from oracle import coracle
+    dev = torch.device("cuda:0")
+    n_docs = args.docs
+    csc = synthetic.zipf_csc(n_docs, VOCAB, 56.0, 42, dev, k1=1.2, b=0.75, method="lucene")
+    sc = BayesianBM25Scorer(method="lucene", alpha=ALPHA, beta=BETA, base_rate=BASE_RATE)
+    sc.index_from_csc(csc)
+    q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, 43)
+    gen = torch.Generator(device=dev).manual_seed(44)
+    # per-(query, doc) cosine input, SURVEY 8d: clip(N(0.2, 0.15), -1, 1) fp32; one [n_docs] row per query
+    cos = torch.clamp(torch.randn((args.queries, n_docs), device=dev, generator=gen) * 0.15 + 0.2, -1, 1)
+    queries = [q_terms[q_off[i]:q_off[i + 1]] for i in range(args.queries)]
+    out = {}
+
+    def run(i, weights=(0.6, 0.4), alpha=0.5):
+        fused = hybrid.hybrid_probabilities_device(sc, queries[i], cos[i], weights, alpha)
+        out[i] = hybrid.topk_device(fused, 100)
+
+    for i in range(min(4, args.queries)):
+        run(i)
+    l0 = _lib.lib().bb25_launch_count()
+    ms = _time(run, args.queries)
+    launches = _lib.lib().bb25_launch_count() - l0
+    # parity on two queries against the oracle's composition of the reference formulas
+    host = _host(csc)
+    params = coracle.make_params(ALPHA, BETA, BASE_RATE)
+    ok = True
+    for i in (0, 1):
+        p_b = coracle.get_probabilities(host, params, queries[i])
+        p_v = coracle.cosine_to_probability(cos[i].cpu().numpy().astype(np.float64))
+        want = coracle.log_odds_conjunction(np.stack([p_b, p_v], -1), alpha=0.5, weights=(0.6, 0.4))
+        w_ids, w_vals = coracle.topk_f64(want, 100)
+        ok &= bool(np.array_equal(out[i][0].cpu().numpy(), w_ids))
+        ok &= bool(np.allclose(out[i][1].cpu().numpy(), w_vals, rtol=1e-9, atol=0))
+    print(json.dumps({
+        "config": "4: hybrid fusion top-100 (BM25 posterior + cosine_to_probability, weights [0.6, 0.4], alpha 0.5)",
+        "docs": n_docs, "queries": args.queries, "value": args.queries / (ms / 1000.0), "unit": "queries/s",
+        "ms_per_query": ms / args.queries, "kernels_per_query": launches / args.queries,
+        "bytes_streamed_per_query": n_docs * (4 + 8 + 8 + 8 * 13), "parity_vs_oracle": ok,
+        "note": "exhaustive: every document gets a fused probability (inactive BM25 enters as 1e-10); cosine rows are an input",
+    }), flush=True)
+
+
+def config5(args):
+    from oracle import coracle
+    dev = torch.device("cuda:0")
+    n_docs = args.mf_docs
+    t0 = time.perf_counter()
+    body = synthetic.zipf_csc(n_docs, VOCAB, 56.0, 42, dev, k1=1.2, b=0.75, method="lucene")
+    title = synthetic.zipf_csc(n_docs, VOCAB, 8.0, 45, dev, k1=1.2, b=0.75, method="lucene", min_len=2)
+    nnz = {"body": int(body["data"].numel()), "title": int(title["data"].numel())}
+    mf = MultiFieldScorer(["title", "body"], alpha="auto", method="lucene")
+    # fixed transform constants per field (index-time estimation is not what is timed here)
+    mf._new_scorer = lambda: BayesianBM25Scorer(method="lucene", alpha=ALPHA, beta=BETA, base_rate=BASE_RATE)
+    mf.index_from_csc({"title": title, "body": body})
+    build_s = time.perf_counter() - t0
+    q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, 43)
+    queries = [q_terms[q_off[i]:q_off[i + 1]] for i in range(args.queries)]
+    out = {}
+
+    def run(i):
+        fused = mf._fused_device([queries[i], queries[i]])
+        out[i] = mf._topk_device(fused, 10)
+
+    for i in range(min(4, args.queries)):
+        run(i)
+    l0 = _lib.lib().bb25_launch_count()
+    ms = _time(run, args.queries)
+    launches = _lib.lib().bb25_launch_count() - l0
+    ok = None
+    if n_docs <= 10_000_000:  # oracle check where the host copy is cheap
+        params = coracle.make_params(ALPHA, BETA, BASE_RATE)
+        hb, ht = _host(body), _host(title)
+        ok = True
+        for i in (0, 1):
+            stack = np.stack([coracle.get_probabilities(ht, params, queries[i]),
+                              coracle.get_probabilities(hb, params, queries[i])], -1)
+            want = coracle.log_odds_conjunction(stack, alpha=0.5, weights=(0.5, 0.5))
+            w_ids, w_vals = coracle.topk_f64(want, 10)
+            ok &= bool(np.array_equal(out[i][0].cpu().numpy(), w_ids))
+            ok &= bool(np.allclose(out[i][1].cpu().numpy(), w_vals, rtol=1e-9, atol=0))
+    print(json.dumps({
+        "config": "5: MultiFieldScorer(title+body) top-10 by fused probability",
+        "docs": n_docs, "nnz": nnz, "queries": args.queries, "value": args.queries / (ms / 1000.0),
+        "unit": "queries/s", "ms_per_query": ms / args.queries, "kernels_per_query": launches / args.queries,
+        "index_build_s": round(build_s, 1), "parity_vs_oracle": ok,
+        "device_gb": torch.cuda.max_memory_allocated() / 1e9,
+        "note": "exhaustive dense passes (one fused traversal per field + dense top-k); block-max pruning of the fused rank key is not built yet",
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True, choices=[4, 5])
+    ap.add_argument("--docs", type=int, default=8_800_000)
+    ap.add_argument("--mf-docs", type=int, default=50_000_000)
+    ap.add_argument("--queries", type=int, default=64)
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    (config4 if a.config == 4 else config5)(a)
