@@ -663,6 +663,26 @@ __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, con
     }
 }
 
+// A head term whose block slice is (nearly) full is cheaper to add from its dense value
+// row: 128-bit row loads and 128-bit shared read-modify-writes, 4 documents per lane per
+// step, instead of walking ~1000 (doc id, value) postings.  Absent documents hold -0.0f,
+// and x + (-0.0f) == x, so the sums stay bit-exact.
+constexpr int kDenseAddMinLen = 768;
+__device__ __forceinline__ void dense_add_warp(const float *__restrict__ row, float4 *acc4, int lane) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll 2
+    for (int i = 0; i < kBlockDocs / 128; i++) {
+        const int w = i * 32 + lane;
+        const float4 r = ld_nc_f4(r4 + w);
+        float4 v = acc4[w];
+        v.x = __fadd_rn(v.x, r.x);
+        v.y = __fadd_rn(v.y, r.y);
+        v.z = __fadd_rn(v.z, r.z);
+        v.w = __fadd_rn(v.w, r.w);
+        acc4[w] = v;
+    }
+}
+
 struct TermEnt {
     long long start;
     int len;
@@ -766,6 +786,7 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                     n_skipped++;
                     continue;
                 }
+                const int dslot = (a.dense_vals && lane < m && e.len > 0) ? a.dense_slot[e.term] : -1;
                 if (MS && a.prune >= 2 && thr_score != 0u) {
                     // ---- MaxScore split of the query's terms for this block -------------------
                     // NE ("non-essential"): head terms with a dense value row whose block maxima,
@@ -774,7 +795,6 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                     // GATHERED only for documents some S term touched.  The NE bound is summed in
                     // ascending order with a 1e-5 relative margin, which dominates the rounding
                     // difference to any other summation order (m <= 32 terms).
-                    const int dslot = (lane < m && e.len > 0) ? a.dense_slot[e.term] : -1;
                     const float thr_val = __uint_as_float(thr_score);
                     unsigned rem = __ballot_sync(0xFFFFFFFFu, dslot >= 0);
                     unsigned ne_mask = 0u;
@@ -843,7 +863,11 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                                 }
                             } else {
                                 const long long s = shfl_ll(e.start, i);
-                                scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                                const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
+                                if (slot >= 0 && len >= kDenseAddMinLen)
+                                    dense_add_warp(a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base, acc4, lane);
+                                else
+                                    scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
                             }
                             __syncwarp();
                         }
@@ -864,7 +888,11 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                 for (int i = 0; i < m; i++) {
                     const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
                     const long long s = shfl_ll(e.start, i);
-                    if (len) scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                    const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
+                    if (slot >= 0 && len >= kDenseAddMinLen)
+                        dense_add_warp(a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base, acc4, lane);
+                    else if (len)
+                        scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
                     __syncwarp();
                 }
             } else {
