@@ -353,7 +353,7 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
         TRY(cudaDeviceSynchronize());
         if (const char *e = getenv("BB25_PRUNE")) {
             const int v = atoi(e);
-            idx->prune = v < 0 ? 0 : (v > 2 ? 2 : v);
+            idx->prune = v < 0 ? 0 : (v > 3 ? 3 : v);
         }
     }
     {

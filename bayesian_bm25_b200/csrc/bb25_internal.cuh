@@ -208,7 +208,7 @@ struct bb25_index {
     //   .y = (fp32 bits of the block maximum, rounded UP to a multiple of 2^11) | posting count (<= 1024)
     uint2 *blk_tab = nullptr;
     int n_blocks = 0;
-    int prune = 2;  // 0 exhaustive, 1 skip (block, query) units under the block-max bound, 2 + MaxScore units
+    int prune = 3;  // 0 exhaustive, 1 block-max skip, 2 + MaxScore units, 3 + candidate-driven queries
     // dense value rows for the most frequent terms (df >= n_docs/8, at most kMaxDenseTerms):
     // dense_vals[slot][doc] = posting value, or -0.0f where absent; O(1) lookup of a head term's
     // contribution to one document, used by the MaxScore path of the block kernel
@@ -225,6 +225,7 @@ struct bb25_index {
     size_t device_bytes = 0;
     // stats of the last retrieve_batch
     int64_t st_launches = 0, st_passes = 0, st_reruns = 0, st_candidates = 0;
+    int64_t st_routed = 0, st_cand_items = 0;  // queries evaluated candidate-by-candidate / their work items
     int64_t st_units = 0, st_units_skipped = 0, st_units_maxscore = 0;  // (block, query) units visited / pruned / MaxScore
     // CUDA-event pairs around the traversal launches of the last retrieve_batch
     static constexpr int kMaxEv = 256;

@@ -861,13 +861,9 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                                     const int o = clist[c];
                                     acc[o] = __fadd_rn(acc[o], ld_nc_f32(dv + o));
                                 }
-                            } else {
+                            } else {  // S terms are short here (s_total <= kMsListCap)
                                 const long long s = shfl_ll(e.start, i);
-                                const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
-                                if (slot >= 0 && len >= kDenseAddMinLen)
-                                    dense_add_warp(a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base, acc4, lane);
-                                else
-                                    scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                                scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
                             }
                             __syncwarp();
                         }
@@ -976,6 +972,215 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t 
     }
     BB25_LAUNCH_CHECK();
     return 0;
+}
+
+
+// =================================================================================
+// Candidate-driven evaluation (pruning level 3, query-level MaxScore).  For a query
+// whose threshold seed exceeds the summed GLOBAL maxima of its most frequent terms,
+// those terms are non-essential for the whole corpus: only documents holding one of the
+// remaining (essential, rare) terms can reach the top-k.  Such a query is routed away
+// from the block traversal: one thread per posting of an essential term evaluates that
+// document completely -- every query term looked up in query order (dense value row, or
+// block-table entry + binary search of the <= 1024-posting slice), the fp32 sum formed
+// in exactly bm25s's order -- and emits it if it passes the threshold.  A document
+// reachable through several essential terms is evaluated by the first of them only.
+// Work is proportional to the essential terms' document frequencies, not to N.
+// =================================================================================
+constexpr int kCandChunk = 1024;  // postings per work item
+
+struct RouteArgs {
+    const int32_t *q_terms;  // sanitised copy
+    const int64_t *q_off;
+    int64_t term_base;
+    int64_t n_q;
+    const unsigned long long *thr;
+    const float *gmax;  // per-term global maximum posting value
+    const int64_t *indptr;
+    long long route_max;  // route only if the essential terms' summed df is <= this
+    uint32_t *ne_mask;    // [n_q] bit i = i-th query term is non-essential
+    int32_t *list_a, *list_b;
+    unsigned int *n_a, *n_b;
+    uint2 *items;  // {query, position << 24 | chunk}
+    unsigned int *n_items;
+    unsigned int items_cap;
+};
+
+__device__ inline unsigned int count_items(const RouteArgs &a, long long t0, int m, uint32_t ne) {
+    unsigned int n = 0;
+    for (int i = 0; i < m; i++)
+        if (!((ne >> i) & 1u)) {
+            const int t = a.q_terms[t0 + i];
+            n += (unsigned int)((a.indptr[t + 1] - a.indptr[t] + kCandChunk - 1) / kCandChunk);
+        }
+    return n;
+}
+__device__ inline void write_items(const RouteArgs &a, int q, long long t0, int m, uint32_t ne, unsigned int base) {
+    for (int i = 0; i < m; i++)
+        if (!((ne >> i) & 1u)) {
+            const int t = a.q_terms[t0 + i];
+            const unsigned int nch = (unsigned int)((a.indptr[t + 1] - a.indptr[t] + kCandChunk - 1) / kCandChunk);
+            for (unsigned int c = 0; c < nch; c++) a.items[base++] = make_uint2((unsigned int)q, ((unsigned int)i << 24) | c);
+        }
+}
+
+// one thread per query: essential / non-essential split against the GLOBAL term maxima,
+// routing decision, work items of the routed queries
+__global__ void route_kernel(const RouteArgs a) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n_q) return;
+    const long long t0 = a.q_off[q] - a.term_base;
+    const int m = (int)max(0ll, (long long)(a.q_off[q + 1] - a.q_off[q]));
+    const float thr_val = __uint_as_float((uint32_t)(a.thr[q] >> 33));
+    uint32_t ne = 0u;
+    bool routed = false;
+    if (m >= 1 && m <= 24 && thr_val > 0.f) {
+        // greedy: take terms in ascending order of their maximum while the running sum,
+        // with a 1e-5 relative margin for the summation order, stays below the threshold
+        float run = 0.f;
+        for (;;) {
+            int best = -1;
+            float bv = 0.f;
+            for (int i = 0; i < m; i++)
+                if (!((ne >> i) & 1u)) {
+                    const float g = a.gmax[a.q_terms[t0 + i]];
+                    if (best < 0 || g < bv) { best = i; bv = g; }
+                }
+            if (best < 0) break;
+            const float cand = __fadd_rn(run, bv);
+            if (!(__fmul_rn(cand, 1.00001f) < thr_val)) break;
+            run = cand;
+            ne |= 1u << best;
+        }
+        if (ne != 0u) {
+            long long w = 0;
+            for (int i = 0; i < m; i++)
+                if (!((ne >> i) & 1u)) {
+                    const int t = a.q_terms[t0 + i];
+                    w += a.indptr[t + 1] - a.indptr[t];
+                }
+            if (w <= a.route_max) {
+                const unsigned int cnt = count_items(a, t0, m, ne);
+                const unsigned int base = atomicAdd(a.n_items, cnt);
+                if (base + cnt <= a.items_cap) {
+                    write_items(a, (int)q, t0, m, ne, base);
+                    routed = true;
+                } else {
+                    atomicSub(a.n_items, cnt);  // does not fit: leave the query to the block traversal
+                }
+            }
+        }
+    }
+    a.ne_mask[q] = routed ? ne : 0u;
+    if (routed) a.list_a[atomicAdd(a.n_a, 1u)] = (int)q;
+    else a.list_b[atomicAdd(a.n_b, 1u)] = (int)q;
+}
+
+// work items again for routed queries whose candidate row overflowed
+__global__ void rebuild_items_kernel(const RouteArgs a, const int32_t *list, int n_list) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_list) return;
+    const int q = list[idx];
+    const long long t0 = a.q_off[q] - a.term_base;
+    const int m = (int)(a.q_off[q + 1] - a.q_off[q]);
+    const uint32_t ne = a.ne_mask[q];
+    const unsigned int cnt = count_items(a, t0, m, ne);
+    const unsigned int base = atomicAdd(a.n_items, cnt);
+    if (base + cnt <= a.items_cap) write_items(a, q, t0, m, ne, base);
+}
+
+struct CandArgs {
+    const float *data;
+    const int32_t *indices;
+    const int64_t *indptr;
+    const uint2 *blk_tab;
+    int64_t n_vocab;
+    const int32_t *dense_slot;
+    const float *dense_vals;
+    int64_t dense_stride;
+    const int32_t *q_terms;
+    const int64_t *q_off;
+    int64_t term_base;
+    const uint32_t *ne_mask;
+    const uint2 *items;
+    const unsigned long long *thr;
+    unsigned int *cand_cnt;
+    unsigned long long *cand_key;
+    int cap;
+};
+
+__global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandArgs a) {
+    __shared__ int s_term[24];
+    __shared__ int s_slot[24];
+    __shared__ long long s_base[24];
+    const uint2 item = a.items[blockIdx.x];
+    const int q = (int)item.x;
+    const int pos = (int)(item.y >> 24);
+    const unsigned int chunk = item.y & 0xFFFFFFu;
+    const long long t0 = a.q_off[q] - a.term_base;
+    const int m = (int)(a.q_off[q + 1] - a.q_off[q]);
+    if (threadIdx.x < m) {
+        const int t = a.q_terms[t0 + threadIdx.x];
+        s_term[threadIdx.x] = t;
+        s_slot[threadIdx.x] = a.dense_slot[t];
+        s_base[threadIdx.x] = a.indptr[t];
+    }
+    __syncthreads();
+    const uint32_t ne = a.ne_mask[q];
+    const unsigned long long thr = a.thr[q];
+    const uint32_t thr_score = (uint32_t)(thr >> 33);
+    const long long ebase = s_base[pos];
+    const long long df = a.indptr[s_term[pos] + 1] - ebase;
+    unsigned int *ccnt = a.cand_cnt + q;
+    unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
+#pragma unroll 1
+    for (int u = 0; u < kCandChunk / 256; u++) {
+        const long long j = (long long)chunk * kCandChunk + u * 256 + threadIdx.x;
+        if (j >= df) break;
+        const uint32_t d = (uint32_t)ld_nc_s32(a.indices + ebase + j);
+        const float ve = ld_nc_f32(a.data + ebase + j);
+        const uint2 *row = a.blk_tab + (size_t)(d >> 10) * (size_t)a.n_vocab;
+        float acc = 0.f;
+        bool dup = false;
+        for (int i = 0; i < m; i++) {
+            if (i == pos) {
+                acc = __fadd_rn(acc, ve);
+                continue;
+            }
+            float val = 0.f;
+            bool present = false;
+            const int slot = s_slot[i];
+            if (slot >= 0) {
+                val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + d];
+                present = __float_as_uint(val) != 0x80000000u;
+            } else {
+                const uint2 ent = row[s_term[i]];
+                const int len = (int)(ent.y & kBlkLenMask);
+                if (len) {
+                    long long lo = s_base[i] + (long long)ent.x;
+                    const long long end = lo + len;
+                    long long hi = end;
+                    while (lo < hi) {
+                        const long long mid = (lo + hi) >> 1;
+                        if ((uint32_t)a.indices[mid] < d) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    if (lo < end && (uint32_t)a.indices[lo] == d) {
+                        present = true;
+                        val = a.data[lo];
+                    }
+                }
+            }
+            if (present) {
+                if (i < pos && !((ne >> i) & 1u)) {  // an earlier essential term owns this document
+                    dup = true;
+                    break;
+                }
+                acc = __fadd_rn(acc, val);
+            }
+        }
+        if (!dup) emit_if_candidate(acc, d, thr_score, thr, ccnt, crow, a.cap);
+    }
 }
 
 // traversal kernel family used by retrieve: BB25_KERNEL=tile selects the CTA-tile kernel
@@ -1153,7 +1358,20 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     const size_t o_la = align_up(o_prev + sizeof(unsigned int) * (size_t)n_q);
     const size_t o_lb = align_up(o_la + sizeof(int32_t) * (size_t)n_q);
     const size_t o_ctr = align_up(o_lb + sizeof(int32_t) * (size_t)n_q);
-    const size_t o_key = align_up(o_ctr + 64);
+    const size_t o_ne = align_up(o_ctr + 128);
+    const size_t o_lista = align_up(o_ne + sizeof(uint32_t) * (size_t)n_q);
+    const size_t o_listb = align_up(o_lista + sizeof(int32_t) * (size_t)n_q);
+    // candidate-path work items: <= route_max / chunk + 24 per query
+    int route_div = 32;
+    if (const char *e = getenv("BB25_ROUTE_DIV")) {
+        const int v = atoi(e);
+        if (v >= 2 && v <= 4096) route_div = v;
+    }
+    const long long route_max = (long long)idx->n_docs / route_div;
+    const bool use_cand = use_block_kernel() && idx->prune >= 3 && idx->dense_slot != nullptr && n_q > 0;
+    const size_t items_cap = use_cand ? (size_t)n_q * (size_t)(route_max / kCandChunk + 25) : 1;
+    const size_t o_items = align_up(o_listb + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_key = align_up(o_items + sizeof(uint2) * items_cap);
     const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
     if (ensure_workspace(idx, total)) return 1;
     unsigned char *ws = (unsigned char *)idx->ws;
@@ -1168,6 +1386,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     int *d_err = (int *)(ws + o_ctr + 16);
     unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
     unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [3]
+    unsigned int *d_route = (unsigned int *)(ws + o_ctr + 64);  // [0] n_a, [1] n_b, [2] n_items
     unsigned long long *d_keys = (unsigned long long *)(ws + o_key);
 
     const float *kth = nullptr;
@@ -1178,7 +1397,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     idx->st_traverse_launches = 0;
     int64_t launches0 = (int64_t)bb25_launch_count();
 
-    BB25_CUDA(cudaMemsetAsync(ws + o_ctr, 0, 64, st));
+    BB25_CUDA(cudaMemsetAsync(ws + o_ctr, 0, 128, st));
     prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(q_terms, q_off, n_q, term_base, idx->n_vocab, kth,
                                                                       d_terms, d_nc, d_thr, d_cnt, d_prev, d_err);
     BB25_LAUNCH_CHECK();
@@ -1269,9 +1488,115 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     unsigned int *h_flags = (unsigned int *)idx->pinned;  // [0] n_over, [1] err
 
-    for (int gi = 0; gi < ng; gi++) {
-        int cur_n = (int)n_q;
-        const int32_t *cur_list = nullptr;
+    idx->st_routed = 0;
+    idx->st_cand_items = 0;
+
+    // ---- candidate-driven queries (pruning level 3) ---------------------------------
+    const int32_t *blk_list = nullptr;  // queries left to the block traversal (nullptr = all)
+    int blk_n = (int)n_q;
+    if (use_cand) {
+        const float *gmax = nullptr;
+        if (get_kth_values(idx, 1, st, &gmax)) return 1;
+        RouteArgs ra{};
+        ra.q_terms = d_terms;
+        ra.q_off = q_off;
+        ra.term_base = term_base;
+        ra.n_q = n_q;
+        ra.thr = d_thr;
+        ra.gmax = gmax;
+        ra.indptr = idx->indptr;
+        ra.route_max = route_max;
+        ra.ne_mask = (uint32_t *)(ws + o_ne);
+        ra.list_a = (int32_t *)(ws + o_lista);
+        ra.list_b = (int32_t *)(ws + o_listb);
+        ra.n_a = d_route;
+        ra.n_b = d_route + 1;
+        ra.items = (uint2 *)(ws + o_items);
+        ra.n_items = d_route + 2;
+        ra.items_cap = (unsigned int)std::min<size_t>(items_cap, 0xFFFFFFF0u);
+        route_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(ra);
+        BB25_LAUNCH_CHECK();
+        unsigned int *h_r = (unsigned int *)idx->pinned + 8;
+        BB25_CUDA(cudaMemcpyAsync(h_r, d_route, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        BB25_CUDA(cudaMemcpyAsync(&h_flags[1], d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BB25_CUDA(cudaStreamSynchronize(st));
+        if (h_flags[1]) {
+            set_error("invalid query batch (flags=%u: 1 term id out of range, 2 q_off not monotone)", h_flags[1]);
+            return 1;
+        }
+        int n_a = (int)h_r[0];
+        unsigned int n_items = h_r[2];
+        blk_list = ra.list_b;
+        blk_n = (int)h_r[1];
+        idx->st_routed = n_a;
+        CandArgs ca{};
+        ca.data = idx->data;
+        ca.indices = idx->indices;
+        ca.indptr = idx->indptr;
+        ca.blk_tab = idx->blk_tab;
+        ca.n_vocab = idx->n_vocab;
+        ca.dense_slot = idx->dense_slot;
+        ca.dense_vals = idx->dense_vals;
+        ca.dense_stride = idx->dense_stride;
+        ca.q_terms = d_terms;
+        ca.q_off = q_off;
+        ca.term_base = term_base;
+        ca.ne_mask = ra.ne_mask;
+        ca.items = ra.items;
+        ca.thr = d_thr;
+        ca.cand_cnt = d_cnt;
+        ca.cand_key = d_keys;
+        ca.cap = cap;
+        const int32_t *a_list = ra.list_a;
+        int flip = 0;
+        for (int iter = 0; n_a > 0; iter++) {
+            if (iter > 200) { set_error("threshold refinement did not converge"); return 1; }
+            const int pair = idx->ev_used < bb25_index::kMaxEv ? idx->ev_used : -1;
+            if (pair >= 0) {
+                while (idx->n_ev < 2 * (pair + 1)) {
+                    BB25_CUDA(cudaEventCreate(&idx->ev[idx->n_ev]));
+                    idx->n_ev++;
+                }
+                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair], st));
+            }
+            if (n_items > 0) {
+                cand_kernel<<<n_items, 256, 0, st>>>(ca);
+                BB25_LAUNCH_CHECK();
+            }
+            if (pair >= 0) {
+                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair + 1], st));
+                idx->ev_used++;
+            }
+            idx->st_cand_items += n_items;
+            idx->st_passes++;
+            BB25_CUDA(cudaMemsetAsync(d_nover, 0, sizeof(unsigned int), st));
+            sa.q_list = a_list;
+            sa.final_pass = 1;
+            sa.over_list = d_list[flip];
+            select_kernel<512><<<(unsigned)n_a, 512, sel_smem, st>>>(sa);
+            BB25_LAUNCH_CHECK();
+            BB25_CUDA(cudaMemcpyAsync(&h_flags[0], d_nover, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            BB25_CUDA(cudaStreamSynchronize(st));
+            const unsigned int n_over = h_flags[0];
+            if (n_over == 0) break;
+            idx->st_reruns += n_over;
+            // tighter thresholds are in place; evaluate those queries' candidates again
+            a_list = d_list[flip];
+            n_a = (int)n_over;
+            flip ^= 1;
+            BB25_CUDA(cudaMemsetAsync(ra.n_items, 0, sizeof(unsigned int), st));
+            rebuild_items_kernel<<<(unsigned)((n_a + 127) / 128), 128, 0, st>>>(ra, a_list, n_a);
+            BB25_LAUNCH_CHECK();
+            BB25_CUDA(cudaMemcpyAsync(h_r, d_route, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            BB25_CUDA(cudaStreamSynchronize(st));
+            n_items = h_r[2];
+        }
+    }
+
+    // ---- block / tile traversal of the remaining queries, group by group -----------
+    for (int gi = 0; gi < ng && blk_n > 0; gi++) {
+        int cur_n = blk_n;
+        const int32_t *cur_list = blk_list;
         int flip = 0;
         for (int iter = 0;; iter++) {
             if (iter > 200) { set_error("threshold refinement did not converge"); return 1; }
@@ -1454,10 +1779,17 @@ int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *un
     return 0;
 }
 
+int bb25_retrieve_route_stats(const bb25_index *idx, int64_t *routed_queries, int64_t *work_items) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (routed_queries) *routed_queries = idx->st_routed;
+    if (work_items) *work_items = idx->st_cand_items;
+    return 0;
+}
+
 int bb25_index_set_pruning(bb25_index *idx, int enable) {
     if (!idx) { set_error("index is NULL"); return 1; }
     std::lock_guard<std::mutex> lock(idx->mu);
-    idx->prune = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+    idx->prune = enable < 0 ? 0 : (enable > 3 ? 3 : enable);
     return 0;
 }
 

@@ -394,10 +394,14 @@ class BayesianBM25Scorer:
         u, sk, ms_ = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().bb25_retrieve_prune_stats(self._handle, C.byref(u), C.byref(sk), C.byref(ms_)))
         out["units"], out["units_skipped"], out["units_maxscore"] = u.value, sk.value, ms_.value
+        rq, wi = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().bb25_retrieve_route_stats(self._handle, C.byref(rq), C.byref(wi)))
+        out["routed_queries"], out["candidate_items"] = rq.value, wi.value
         return out
 
     def set_pruning(self, level: int) -> None:
         """Dynamic pruning level of batch retrieve: 0 exhaustive, 1 block-max skip,
-        2 block-max skip + MaxScore (default).  Results are identical at every level."""
+        2 + MaxScore units, 3 + candidate-driven evaluation of rare-term queries (default).
+        Results are identical at every level."""
         self._require_index("set_pruning()")
         _lib.check(_lib.lib().bb25_index_set_pruning(self._handle, int(level)))

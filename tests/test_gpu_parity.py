@@ -191,7 +191,7 @@ def _queries_with_edge_cases(vocab, seed):
 
 
 @pytest.mark.parametrize("kernel,tile_docs,prune", [
-    ("block", 8192, 2), ("block", 8192, 1), ("block", 8192, 0), ("tile", 8192, 1), ("tile", 16384, 1),
+    ("block", 8192, 3), ("block", 8192, 2), ("block", 8192, 1), ("block", 8192, 0), ("tile", 8192, 1), ("tile", 16384, 1),
     ("tile", 32768, 1)])
 def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
     """Both traversal kernels (warp-private blocks at every pruning level -- exhaustive,
@@ -226,6 +226,10 @@ def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
                 assert st["units_skipped"] > 0, st  # a top-1 threshold prunes most blocks
             if prune == 2 and k <= 100:
                 assert st["units_maxscore"] > 0, st
+            if prune == 3 and k <= 100:
+                assert st["routed_queries"] > 0 and st["candidate_items"] > 0, st
+            if prune < 3:
+                assert st["routed_queries"] == 0, st
             if prune < 2:
                 assert st["units_maxscore"] == 0, st
     # dense surfaces
