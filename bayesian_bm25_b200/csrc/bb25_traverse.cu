@@ -1107,12 +1107,14 @@ struct CandArgs {
     unsigned int *cand_cnt;
     unsigned long long *cand_key;
     int cap;
+    const float *gmax;
 };
 
 __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandArgs a) {
     __shared__ int s_term[24];
     __shared__ int s_slot[24];
     __shared__ long long s_base[24];
+    __shared__ float s_rest[25];  // s_rest[i] = sum of the global maxima of terms at positions >= i, except `pos`
     const uint2 item = a.items[blockIdx.x];
     const int q = (int)item.x;
     const int pos = (int)(item.y >> 24);
@@ -1126,9 +1128,19 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
         s_base[threadIdx.x] = a.indptr[t];
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = 0.f;
+        s_rest[m] = 0.f;
+        for (int i = m - 1; i >= 0; i--) {
+            if (i != pos) r = __fadd_rn(r, a.gmax[s_term[i]]);
+            s_rest[i] = r;
+        }
+    }
+    __syncthreads();
     const uint32_t ne = a.ne_mask[q];
     const unsigned long long thr = a.thr[q];
     const uint32_t thr_score = (uint32_t)(thr >> 33);
+    const float thr_val = __uint_as_float(thr_score);
     const long long ebase = s_base[pos];
     const long long df = a.indptr[s_term[pos] + 1] - ebase;
     unsigned int *ccnt = a.cand_cnt + q;
@@ -1139,6 +1151,9 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
         if (j >= df) break;
         const uint32_t d = (uint32_t)ld_nc_s32(a.indices + ebase + j);
         const float ve = ld_nc_f32(a.data + ebase + j);
+        // MaxScore bound: own value + the other terms' global maxima (1e-5 relative margin
+        // for the summation order); tightened term by term as actual values replace maxima
+        if (__fmul_rn(__fadd_rn(ve, s_rest[0]), 1.00001f) < thr_val) continue;
         const uint2 *row = a.blk_tab + (size_t)(d >> 10) * (size_t)a.n_vocab;
         float acc = 0.f;
         bool dup = false;
@@ -1146,6 +1161,13 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
             if (i == pos) {
                 acc = __fadd_rn(acc, ve);
                 continue;
+            }
+            {
+                const float rest = i < pos ? __fadd_rn(s_rest[i], ve) : s_rest[i];
+                if (__fmul_rn(__fadd_rn(acc, rest), 1.00001f) < thr_val) {
+                    dup = true;  // cannot reach the threshold any more
+                    break;
+                }
             }
             float val = 0.f;
             bool present = false;
@@ -1547,6 +1569,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         ca.cand_cnt = d_cnt;
         ca.cand_key = d_keys;
         ca.cap = cap;
+        ca.gmax = gmax;
         const int32_t *a_list = ra.list_a;
         int flip = 0;
         for (int iter = 0; n_a > 0; iter++) {
