@@ -629,7 +629,15 @@ __device__ __forceinline__ long long shfl_ll(long long v, int src) {
     return ((long long)hi << 32) | (unsigned int)lo;
 }
 
+// acc[o] (+)= v.  FRESH: the accumulators are known to be all zero (first term of the
+// unit), so the read half of the read-modify-write is dropped; v + 0.0f keeps -0.0f out.
+template <bool FRESH>
+__device__ __forceinline__ void acc_add(float *acc, int o, float v) {
+    acc[o] = FRESH ? __fadd_rn(v, 0.0f) : __fadd_rn(acc[o], v);
+}
+
 // postings [s, s+len) of one term, len <= 1024, into the warp's block accumulators
+template <bool FRESH = false>
 __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, const int32_t *__restrict__ indices,
                                              long long s, int len, float *acc, int doc_base, int lane) {
     int head = (int)((32 - (s & 31)) & 31);  // elements before the first 128-byte boundary
@@ -637,7 +645,7 @@ __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, con
     if (lane < head) {
         const long long j = s + lane;
         const int o = ld_nc_s32(indices + j) - doc_base;
-        acc[o] = __fadd_rn(acc[o], ld_nc_f32(data + j));
+        acc_add<FRESH>(acc, o, ld_nc_f32(data + j));
     }
     const int n = len - head;
     const int32_t *ip = indices + s + head;
@@ -652,14 +660,11 @@ __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, con
             v[u] = ld_nc_f32(dp + j + 32 * u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int o = d[u] - doc_base;
-            acc[o] = __fadd_rn(acc[o], v[u]);
-        }
+        for (int u = 0; u < 4; u++) acc_add<FRESH>(acc, d[u] - doc_base, v[u]);
     }
     for (; j < n; j += 32) {
         const int o = ld_nc_s32(ip + j) - doc_base;
-        acc[o] = __fadd_rn(acc[o], ld_nc_f32(dp + j));
+        acc_add<FRESH>(acc, o, ld_nc_f32(dp + j));
     }
 }
 
@@ -667,14 +672,15 @@ __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, con
 // row: 128-bit row loads and 128-bit shared read-modify-writes, 4 documents per lane per
 // step, instead of walking ~1000 (doc id, value) postings.  Absent documents hold -0.0f,
 // and x + (-0.0f) == x, so the sums stay bit-exact.
-constexpr int kDenseAddMinLen = 768;
+constexpr int kDenseAddMinLen = 512;
+template <bool FRESH = false>
 __device__ __forceinline__ void dense_add_warp(const float *__restrict__ row, float4 *acc4, int lane) {
     const float4 *r4 = reinterpret_cast<const float4 *>(row);
 #pragma unroll 2
     for (int i = 0; i < kBlockDocs / 128; i++) {
         const int w = i * 32 + lane;
         const float4 r = ld_nc_f4(r4 + w);
-        float4 v = acc4[w];
+        float4 v = FRESH ? make_float4(0.f, 0.f, 0.f, 0.f) : acc4[w];  // FRESH: accumulators are all zero
         v.x = __fadd_rn(v.x, r.x);
         v.y = __fadd_rn(v.y, r.y);
         v.z = __fadd_rn(v.z, r.z);
@@ -881,14 +887,21 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                         continue;
                     }
                 }
+                bool fresh = true;  // accumulators all zero until the first term with postings here
                 for (int i = 0; i < m; i++) {
                     const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
                     const long long s = shfl_ll(e.start, i);
                     const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
-                    if (slot >= 0 && len >= kDenseAddMinLen)
-                        dense_add_warp(a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base, acc4, lane);
-                    else if (len)
-                        scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                    if (!len) continue;
+                    if (slot >= 0 && len >= kDenseAddMinLen) {
+                        const float *row_v = a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base;
+                        if (fresh) dense_add_warp<true>(row_v, acc4, lane);
+                        else dense_add_warp<false>(row_v, acc4, lane);
+                    } else {
+                        if (fresh) scatter_warp<true>(a.data, a.indices, s, len, acc, doc_base, lane);
+                        else scatter_warp<false>(a.data, a.indices, s, len, acc, doc_base, lane);
+                    }
+                    fresh = false;
                     __syncwarp();
                 }
             } else {

@@ -6,8 +6,8 @@ without the per-document Python loop, so an 8.8 M-document corpus is indexed in
 seconds.  The posting values follow bm25s's arithmetic operation by operation
 (NumPy-2 promotion rules: the per-document length term is a float64 scalar, so the
 term-frequency component is evaluated in float64 and the product with the fp32 idf
-is rounded to fp32 once) -- tests/test_index_build.py checks bit-equality against the
-per-document restatement in oracle/bm25s_equiv.py for all three variants.
+is rounded to fp32 once) -- tests/test_host_logic.py checks bit-equality against an
+independent per-document restatement for all three variants.
 
 Runs on whatever device the input tensors live on (CUDA in production and in the
 benchmark; CPU in the unit tests).  This is index-time code, not the query path.

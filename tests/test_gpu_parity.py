@@ -245,6 +245,42 @@ def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
     np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
 
 
+def test_host_buffer_entry_point_and_pruning_levels():
+    """bb25_retrieve_batch_host (the C-ABI call with HOST buffers that INTEGRATION.md binds) and
+    bb25_index_set_pruning on one handle: every level returns the oracle's result."""
+    pkg = _pkg()
+    from bayesian_bm25_b200 import _lib, synthetic
+    from oracle import coracle
+    n_docs, vocab, k = 90_000, 3000, 50
+    csc = synthetic.zipf_csc(n_docs, vocab, 40.0, seed=61, device=torch.device("cuda:0"))
+    host = _host(csc)
+    sc = pkg.BayesianBM25Scorer(alpha=1.9, beta=0.25, base_rate=0.04)
+    sc.index_from_csc(csc)
+    flat, off = synthetic.zipf_queries(200, vocab, seed=62)
+    params = coracle.make_params(1.9, 0.25, 0.04)
+    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
+    p = _lib.make_params(1.9, 0.25, 0.04)
+    seen = {}
+    for level in (0, 1, 2, 3):
+        sc.set_pruning(level)
+        ids = np.empty((200, k), np.int64); scs = np.empty((200, k), np.float32); prs = np.empty((200, k), np.float64)
+        _lib.check(_lib.lib().bb25_retrieve_batch_host(sc._handle, C.byref(p), flat.ctypes.data, off.ctypes.data, 200, k,
+                                                       ids.ctypes.data, scs.ctypes.data, prs.ctypes.data))
+        np.testing.assert_array_equal(ids, o_ids, err_msg=f"level {level}")
+        np.testing.assert_array_equal(scs.view(np.uint32), o_sc.view(np.uint32))
+        np.testing.assert_allclose(prs, o_pr, rtol=0, atol=PROB_TOL)
+        seen[level] = sc.stats()
+    assert seen[0]["units_skipped"] == 0 and seen[0]["units_maxscore"] == 0 and seen[0]["routed_queries"] == 0
+    assert seen[1]["units_skipped"] > 0 and seen[1]["units_maxscore"] == 0
+    assert seen[2]["units_maxscore"] > 0 and seen[2]["routed_queries"] == 0
+    assert seen[3]["routed_queries"] > 0 and seen[3]["units"] < seen[2]["units"]
+    # scores output may be omitted (NULL)
+    ids = np.empty((200, k), np.int64); prs = np.empty((200, k), np.float64)
+    _lib.check(_lib.lib().bb25_retrieve_batch_host(sc._handle, C.byref(p), flat.ctypes.data, off.ctypes.data, 200, k,
+                                                   ids.ctypes.data, None, prs.ctypes.data))
+    np.testing.assert_array_equal(ids, o_ids)
+
+
 def test_massive_ties_force_threshold_refinement():
     """Every document holds the same single term with the same value: all N keys tie on
     the score, the candidate rows overflow and the 64-bit key threshold must converge."""

@@ -177,3 +177,13 @@ def test_shard_csc_scores_match_unsharded():
         hs = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in sh.items()}
         parts.append(coracle.get_scores(hs, q))
     np.testing.assert_array_equal(np.concatenate(parts), full)
+
+
+def test_product_never_touches_the_oracle():
+    """The shipped package must not import, load or execute anything under oracle/."""
+    pkg_dir = os.path.join(ROOT, "bayesian_bm25_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text, f"{f} mentions the oracle"
