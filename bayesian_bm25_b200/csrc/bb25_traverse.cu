@@ -733,34 +733,8 @@ __device__ __forceinline__ void emit_if_candidate(float v, uint32_t local_id, ui
     }
 }
 
-// Last term of a unit served from a dense row: add, run the epilogue on the sums while
-// they are still in registers, and leave the accumulators zero -- the sums are never
-// written back and never re-read.  FRESH: the accumulators were all zero before.
-template <bool FRESH>
-__device__ __forceinline__ void dense_add_epilogue_warp(const float *__restrict__ row, float4 *acc4, int doc_base,
-                                                        uint32_t thr_score, unsigned long long thr,
-                                                        unsigned int *ccnt, unsigned long long *crow, int cap,
-                                                        int lane) {
-    const float4 *r4 = reinterpret_cast<const float4 *>(row);
-#pragma unroll 2
-    for (int i = 0; i < kBlockDocs / 128; i++) {
-        const int w = i * 32 + lane;
-        const float4 r = ld_nc_f4(r4 + w);
-        float4 v = FRESH ? make_float4(0.f, 0.f, 0.f, 0.f) : acc4[w];
-        if (!FRESH) acc4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v.x = __fadd_rn(v.x, r.x);
-        v.y = __fadd_rn(v.y, r.y);
-        v.z = __fadd_rn(v.z, r.z);
-        v.w = __fadd_rn(v.w, r.w);
-        emit_if_candidate(v.x, (uint32_t)(doc_base + w * 4 + 0), thr_score, thr, ccnt, crow, cap);
-        emit_if_candidate(v.y, (uint32_t)(doc_base + w * 4 + 1), thr_score, thr, ccnt, crow, cap);
-        emit_if_candidate(v.z, (uint32_t)(doc_base + w * 4 + 2), thr_score, thr, ccnt, crow, cap);
-        emit_if_candidate(v.w, (uint32_t)(doc_base + w * 4 + 3), thr_score, thr, ccnt, crow, cap);
-    }
-}
-
-template <int WARPS, bool MS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) block_kernel(const __grid_constant__ BlockArgs a) {
+template <int WARPS, bool MS>
+__global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -914,8 +888,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) block_kernel(const __grid_co
                     }
                 }
                 bool fresh = true;  // accumulators all zero until the first term with postings here
-                bool done = false;  // epilogue already fused into the last term
-                const int last_i = 31 - __clz(__ballot_sync(0xFFFFFFFFu, e.len > 0));
                 for (int i = 0; i < m; i++) {
                     const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
                     const long long s = shfl_ll(e.start, i);
@@ -923,17 +895,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) block_kernel(const __grid_co
                     if (!len) continue;
                     if (slot >= 0 && len >= kDenseAddMinLen) {
                         const float *row_v = a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base;
-                        if (i == last_i) {
-                            unsigned int *fcnt = a.cand_cnt + q;
-                            unsigned long long *frow = a.cand_key + (size_t)q * (size_t)a.cap;
-                            if (fresh) dense_add_epilogue_warp<true>(row_v, acc4, doc_base, thr_score, thr, fcnt, frow, a.cap, lane);
-                            else dense_add_epilogue_warp<false>(row_v, acc4, doc_base, thr_score, thr, fcnt, frow, a.cap, lane);
-                            done = true;
-                        } else if (fresh) {
-                            dense_add_warp<true>(row_v, acc4, lane);
-                        } else {
-                            dense_add_warp<false>(row_v, acc4, lane);
-                        }
+                        if (fresh) dense_add_warp<true>(row_v, acc4, lane);
+                        else dense_add_warp<false>(row_v, acc4, lane);
                     } else {
                         if (fresh) scatter_warp<true>(a.data, a.indices, s, len, acc, doc_base, lane);
                         else scatter_warp<false>(a.data, a.indices, s, len, acc, doc_base, lane);
@@ -941,7 +904,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) block_kernel(const __grid_co
                     fresh = false;
                     __syncwarp();
                 }
-                if (done) continue;
             } else {
                 // long query: bound first (one pass over the entries), then the adds
                 float ub = 0.f;
@@ -1006,25 +968,20 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t 
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
     const bool ms = a.prune >= 2 && a.dense_vals != nullptr;
     const size_t smem = (size_t)BK_WARPS * (ms ? warp_smem_bytes<true>() : warp_smem_bytes<false>());
-    // resident CTAs per SM: 5 (48 registers, no spills) measured against 6 (40 registers)
-    int per_sm = 5;
-    if (!ms) {
-        if (const char *e = getenv("BB25_MINB")) {
-            if (atoi(e) == 6) per_sm = 6;
-        }
+    int per_sm = ms ? 5 : 6;
+    if (const char *e = getenv("BB25_CTAS_PER_SM")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= per_sm) per_sm = v;
     }
     long long grid = (long long)idx->sm_count * per_sm;
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
     if (ms) {
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        block_kernel<BK_WARPS, true, 5><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
-    } else if (per_sm == 6) {
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        block_kernel<BK_WARPS, false, 6><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        block_kernel<BK_WARPS, true><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
     } else {
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        block_kernel<BK_WARPS, false, 5><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        block_kernel<BK_WARPS, false><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
     }
     BB25_LAUNCH_CHECK();
     return 0;
