@@ -49,33 +49,68 @@ def merge_topk_device(ids: torch.Tensor, scores: torch.Tensor, probs: torch.Tens
 
 
 class ShardedRetriever:
-    """Wraps a rank-local BayesianBM25Scorer (indexed on this rank's shard)."""
+    """Wraps a rank-local BayesianBM25Scorer (indexed on this rank's shard).
 
-    def __init__(self, scorer, group=None, profile: bool = False):
+    The query batch is processed in `n_chunks` sub-batches: while the traversal of
+    sub-batch i+1 runs on the main stream, the all-gather + merge of sub-batch i runs
+    on a second stream (NCCL over NVLink), so the exchange step hides behind compute.
+    """
+
+    def __init__(self, scorer, group=None, profile: bool = False, n_chunks: int = 2):
         self.scorer = scorer
         self.group = group
         self.profile = profile
+        self.n_chunks = max(1, int(n_chunks))
         self.timing = {"local_ms": 0.0, "gather_ms": 0.0, "merge_ms": 0.0, "calls": 0}
+        self._comm_stream = None
+
+    def _exchange(self, ids, sc, pr):
+        g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
+        return merge_topk_device(g_ids, g_sc, g_pr)
 
     def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
         sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (self.profile and sharded) else None
-        if ev:
-            ev[0].record()
-        ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k)
         if not sharded:
-            return ids, sc, pr
-        if ev:
-            ev[1].record()
-        g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
-        if ev:
-            ev[2].record()
-        out = merge_topk_device(g_ids, g_sc, g_pr)
-        if ev:
-            ev[3].record()
-            ev[3].synchronize()
-            self.timing["local_ms"] += ev[0].elapsed_time(ev[1])
-            self.timing["gather_ms"] += ev[1].elapsed_time(ev[2])
-            self.timing["merge_ms"] += ev[2].elapsed_time(ev[3])
-            self.timing["calls"] += 1
-        return out
+            return self.scorer.retrieve_ids_device(q_terms, q_off, k)
+        nq = q_off.numel() - 1
+        n_chunks = min(self.n_chunks, max(1, nq // 256))
+        if self.profile or n_chunks == 1:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None
+            if ev:
+                ev[0].record()
+            ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k)
+            if ev:
+                ev[1].record()
+            g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
+            if ev:
+                ev[2].record()
+            out = merge_topk_device(g_ids, g_sc, g_pr)
+            if ev:
+                ev[3].record()
+                ev[3].synchronize()
+                self.timing["local_ms"] += ev[0].elapsed_time(ev[1])
+                self.timing["gather_ms"] += ev[1].elapsed_time(ev[2])
+                self.timing["merge_ms"] += ev[2].elapsed_time(ev[3])
+                self.timing["calls"] += 1
+            return out
+        # pipelined: exchange of sub-batch i on the side stream, traversal of i+1 on the main one
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=q_off.device)
+        main = torch.cuda.current_stream()
+        bounds = [nq * c // n_chunks for c in range(n_chunks + 1)]
+        outs = []
+        for c in range(n_chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off[lo:hi + 1], k)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(done)
+                for t in (ids, sc, pr):
+                    t.record_stream(self._comm_stream)
+                outs.append(self._exchange(ids, sc, pr))
+        main.wait_stream(self._comm_stream)
+        for o in outs:
+            for t in o:
+                t.record_stream(main)
+        return tuple(torch.cat([o[j] for o in outs], dim=0) for j in range(3))
