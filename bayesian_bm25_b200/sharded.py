@@ -63,6 +63,18 @@ class ShardedRetriever:
         self.n_chunks = max(1, int(n_chunks))
         self.timing = {"local_ms": 0.0, "gather_ms": 0.0, "merge_ms": 0.0, "calls": 0}
         self._comm_stream = None
+        self._stats: dict = {}
+
+    def stats(self) -> dict:
+        """Counters of the last retrieve_ids_device call, summed over its sub-batches."""
+        return dict(self._stats)
+
+    def _add_stats(self, reset: bool = False):
+        st = self.scorer.stats()
+        if reset or not self._stats:
+            self._stats = st
+        else:
+            self._stats = {k: self._stats.get(k, 0) + v for k, v in st.items()}
 
     def _exchange(self, ids, sc, pr):
         g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
@@ -71,7 +83,9 @@ class ShardedRetriever:
     def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
         sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
         if not sharded:
-            return self.scorer.retrieve_ids_device(q_terms, q_off, k)
+            out = self.scorer.retrieve_ids_device(q_terms, q_off, k)
+            self._add_stats(reset=True)
+            return out
         nq = q_off.numel() - 1
         n_chunks = min(self.n_chunks, max(1, nq // 256))
         if self.profile or n_chunks == 1:
@@ -79,6 +93,7 @@ class ShardedRetriever:
             if ev:
                 ev[0].record()
             ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k)
+            self._add_stats(reset=True)
             if ev:
                 ev[1].record()
             g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
@@ -102,6 +117,7 @@ class ShardedRetriever:
         for c in range(n_chunks):
             lo, hi = bounds[c], bounds[c + 1]
             ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off[lo:hi + 1], k)
+            self._add_stats(reset=(c == 0))
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(self._comm_stream):

@@ -270,7 +270,7 @@ def main():
         ev0.record()
         for _ in range(args.steps):
             out = step()
-            st = scorer.stats()
+            st = retr.stats()
             for key in acc:
                 acc[key] += st[key]
         ev1.record()
