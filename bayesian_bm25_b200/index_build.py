@@ -42,12 +42,11 @@ def idf_table(method: str, df: np.ndarray, n_docs: int) -> np.ndarray:
     return out
 
 
-def csc_from_sorted_keys(keys: torch.Tensor, n_docs: int, n_vocab: int, doc_len: torch.Tensor,
-                         k1: float, b: float, method: str) -> dict:
-    """keys: SORTED int64 tensor of ``term * n_docs + doc`` for every token
-    occurrence.  doc_len: int64/int32 [n_docs] token counts."""
-    if method not in VALID_METHODS:
-        raise ValueError(f"method must be one of {VALID_METHODS}, got {method!r}")
+def csc_piece(keys: torch.Tensor, n_docs: int, n_vocab: int, doc_len_dev: torch.Tensor, l_avg: float,
+              k1: float, b: float, method: str):
+    """Postings of the terms covered by `keys` (SORTED ``term * n_docs + doc``, one entry per
+    token occurrence): (values fp32, doc ids int32, df int64[n_vocab]).  Terms never straddle
+    pieces, so a piece's document frequencies (hence idf) are complete."""
     dev = keys.device
     uniq, tf = torch.unique_consecutive(keys, return_counts=True)
     del keys
@@ -55,15 +54,10 @@ def csc_from_sorted_keys(keys: torch.Tensor, n_docs: int, n_vocab: int, doc_len:
     doc = uniq - term * n_docs
     del uniq
     df = torch.bincount(term, minlength=n_vocab)
-    indptr = torch.zeros(n_vocab + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(df, 0, out=indptr[1:])
-    total_tokens = int(doc_len.sum().item())
-    l_avg = total_tokens / n_docs  # == np.array(lens).mean(): exact integer sum, one division
     idf = torch.from_numpy(idf_table(method, df.cpu().numpy(), n_docs)).to(dev)
-
     tf32 = tf.to(torch.float32)
     del tf
-    l_d = doc_len.to(dev)[doc].to(torch.float64)
+    l_d = doc_len_dev[doc].to(torch.float64)
     # k1 * ((1 - b) + b * l_d / l_avg)   -- same association as bm25s
     x = (l_d * b) / l_avg
     x = (1 - b) + x
@@ -76,15 +70,38 @@ def csc_from_sorted_keys(keys: torch.Tensor, n_docs: int, n_vocab: int, doc_len:
     else:
         tfc = tf64 / (x + tf64)
     vals = (idf[term].to(torch.float64) * tfc).to(torch.float32)
+    return vals, doc.to(torch.int32), df
+
+
+def csc_from_pieces(pieces, n_docs: int, n_vocab: int, doc_len: torch.Tensor, l_avg: float) -> dict:
+    """Assemble pieces (in ascending term order) into the CSC dict."""
+    dev = pieces[0][0].device
+    df = pieces[0][2].clone()
+    for p in pieces[1:]:
+        df += p[2]
+    indptr = torch.zeros(n_vocab + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(df, 0, out=indptr[1:])
     return {
-        "data": vals,
-        "indices": doc.to(torch.int32),
+        "data": torch.cat([p[0] for p in pieces]) if len(pieces) > 1 else pieces[0][0],
+        "indices": torch.cat([p[1] for p in pieces]) if len(pieces) > 1 else pieces[0][1],
         "indptr": indptr,
         "doc_len": doc_len.to(torch.int32).to(dev),
         "num_docs": n_docs,
         "n_vocab": n_vocab,
         "avgdl": float(l_avg),
     }
+
+
+def csc_from_sorted_keys(keys: torch.Tensor, n_docs: int, n_vocab: int, doc_len: torch.Tensor,
+                         k1: float, b: float, method: str) -> dict:
+    """keys: SORTED int64 tensor of ``term * n_docs + doc`` for every token
+    occurrence.  doc_len: int64/int32 [n_docs] token counts."""
+    if method not in VALID_METHODS:
+        raise ValueError(f"method must be one of {VALID_METHODS}, got {method!r}")
+    total_tokens = int(doc_len.sum().item())
+    l_avg = total_tokens / n_docs  # == np.array(lens).mean(): exact integer sum, one division
+    piece = csc_piece(keys, n_docs, n_vocab, doc_len.to(keys.device), l_avg, k1, b, method)
+    return csc_from_pieces([piece], n_docs, n_vocab, doc_len, l_avg)
 
 
 def build_csc(token_ids: torch.Tensor, doc_offsets: torch.Tensor, n_vocab: int, k1: float = 1.5,

@@ -101,10 +101,49 @@ def zipf_queries(n_queries: int, vocab_size: int, seed: int):
 
 
 def zipf_csc(n_docs: int, vocab_size: int, avg_doc_len: float, seed: int, device, k1=1.2, b=0.75,
-             method="lucene", min_len: int = 5) -> dict:
-    """Synthetic corpus -> CSC tensors on `device` (term ids are Zipf ranks)."""
-    from .index_build import csc_from_sorted_keys
+             method="lucene", min_len: int = 5, n_buckets: int | None = None) -> dict:
+    """Synthetic corpus -> CSC tensors on `device` (term ids are Zipf ranks).
+
+    Corpora with more than ~2^31 tokens cannot go through one torch.sort; they are built
+    in `n_buckets` term-range pieces (a term's tokens never straddle pieces, the pieces
+    concatenate to the same CSC).  n_buckets=None picks 1 or as many as needed."""
+    from .index_build import VALID_METHODS, csc_from_pieces, csc_from_sorted_keys, csc_piece
 
     dl = zipf_doc_lengths(n_docs, avg_doc_len, seed, min_len)
-    keys = zipf_sorted_keys(n_docs, vocab_size, dl, seed, device)
-    return csc_from_sorted_keys(keys, n_docs, vocab_size, torch.from_numpy(dl).to(device), k1, b, method)
+    total = int(dl.sum())
+    if n_buckets is None:
+        n_buckets = 1 if total < (1 << 30) else int(np.ceil(total / float(1 << 29)))
+    if n_buckets <= 1:
+        keys = zipf_sorted_keys(n_docs, vocab_size, dl, seed, device)
+        return csc_from_sorted_keys(keys, n_docs, vocab_size, torch.from_numpy(dl).to(device), k1, b, method)
+    if method not in VALID_METHODS:
+        raise ValueError(f"method must be one of {VALID_METHODS}, got {method!r}")
+    cdf_np = zipf_cdf(vocab_size)
+    # term cut points of (roughly) equal token mass; the head term alone holds ~9 %
+    cuts = [0] + [int(np.searchsorted(cdf_np, (i + 1) / n_buckets)) + 1 for i in range(n_buckets - 1)] + [vocab_size]
+    cuts = sorted(set(min(max(c, 0), vocab_size) for c in cuts))
+    cdf = torch.from_numpy(cdf_np).to(device)
+    offs = np.zeros(n_docs + 1, dtype=np.int64)
+    np.cumsum(dl, out=offs[1:])
+    offs_t = torch.from_numpy(offs).to(device)
+    dl_dev = torch.from_numpy(dl).to(device)
+    l_avg = total / n_docs
+    chunk = 1 << 26
+    pieces = []
+    for t_lo, t_hi in zip(cuts[:-1], cuts[1:]):
+        parts = []
+        for s in range(0, total, chunk):
+            e = min(total, s + chunk)
+            pos = torch.arange(s, e, device=device, dtype=torch.int64)
+            term = torch.searchsorted(cdf, hash_uniform(seed, pos)).clamp_(max=vocab_size - 1)
+            m = (term >= t_lo) & (term < t_hi)
+            pos, term = pos[m], term[m]
+            doc = torch.searchsorted(offs_t, pos, right=True) - 1
+            parts.append(term * n_docs + doc)
+            del pos, term, doc, m
+        keys = torch.cat(parts)
+        del parts
+        keys, _ = torch.sort(keys)
+        pieces.append(csc_piece(keys, n_docs, vocab_size, dl_dev, l_avg, k1, b, method))
+        del keys
+    return csc_from_pieces(pieces, n_docs, vocab_size, dl_dev, l_avg)

@@ -165,6 +165,16 @@ def test_hash_rng_and_zipf_csc_cpu():
     assert len(keys) == dl.sum()
 
 
+def test_bucketed_index_build_equals_single_sort():
+    """The term-range bucketed build (used above 2^31 tokens) gives the identical CSC."""
+    one = synthetic.zipf_csc(3000, 400, 25.0, seed=8, device=torch.device("cpu"))
+    for nb in (2, 5):
+        many = synthetic.zipf_csc(3000, 400, 25.0, seed=8, device=torch.device("cpu"), n_buckets=nb)
+        for key in ("data", "indices", "indptr", "doc_len"):
+            assert torch.equal(one[key], many[key]), (nb, key)
+        assert one["avgdl"] == many["avgdl"]
+
+
 def test_shard_csc_scores_match_unsharded():
     csc = synthetic.zipf_csc(3000, 400, 25.0, seed=2, device=torch.device("cpu"))
     host = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in csc.items()}
