@@ -127,6 +127,19 @@ def config5(args):
             w_ids, w_vals = coracle.topk_f64(want, 10)
             ok &= bool(np.array_equal(out[i][0].cpu().numpy(), w_ids))
             ok &= bool(np.allclose(out[i][1].cpu().numpy(), w_vals, rtol=1e-9, atol=0))
+    else:
+        # too large to copy to the host: check the first 500 k documents against the oracle (posting
+        # values carry the global statistics, so a document-range slice scores independently)
+        from bayesian_bm25_b200 import index_build
+        params = coracle.make_params(ALPHA, BETA, BASE_RATE)
+        hb, ht = _host(index_build.shard_csc(body, 0, 500_000)), _host(index_build.shard_csc(title, 0, 500_000))
+        ok = True
+        for i in (0, 1):
+            stack = np.stack([coracle.get_probabilities(ht, params, queries[i]),
+                              coracle.get_probabilities(hb, params, queries[i])], -1)
+            want = coracle.log_odds_conjunction(stack, alpha=0.5, weights=(0.5, 0.5))
+            got = mf._fused_device([queries[i], queries[i]])[:500_000].cpu().numpy()
+            ok &= bool(np.allclose(got, want, rtol=1e-9, atol=1e-300))
     print(json.dumps({
         "config": "5: MultiFieldScorer(title+body) top-10 by fused probability",
         "docs": n_docs, "nnz": nnz, "queries": args.queries, "value": args.queries / (ms / 1000.0),
