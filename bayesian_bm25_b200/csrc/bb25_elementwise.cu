@@ -217,21 +217,34 @@ __global__ void __launch_bounds__(NT) merge_kernel(const int64_t *__restrict__ i
 __global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const unsigned long long *state,
                                  int shift, int bits, int phase, unsigned int *hist) {
     __shared__ unsigned int sh[2048];
+    if (phase == 1 && state[7]) return;  // every tie on the threshold value is taken: nothing to select
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const unsigned long long prefix = state[0], mask = state[1];
     const unsigned long long iprefix = state[3], imask = state[4];
     const unsigned int dm = (1u << bits) - 1u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
-        if (phase == 0) {
-            if ((b & mask) == prefix) atomicAdd(&sh[(unsigned int)(b >> shift) & dm], 1u);
-        } else {
-            // ties on the threshold value: select the smallest indices (digit of ~index)
-            const unsigned long long inv = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
-            if (b == prefix && (inv & imask) == iprefix) atomicAdd(&sh[(unsigned int)(inv >> shift) & dm], 1u);
+    // block-uniform trip count: the warp-wide match below needs converged warps.  Equal
+    // values are the norm here (every unmatched document carries the same fused
+    // probability), so equal digits are aggregated per warp before touching the histogram.
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        bool in = false;
+        unsigned int digit = 0u;
+        if (i < n) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+            if (phase == 0) {
+                in = (b & mask) == prefix;
+                digit = (unsigned int)(b >> shift) & dm;
+            } else {
+                // ties on the threshold value: select the smallest indices (digit of ~index)
+                const unsigned long long inv = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
+                in = b == prefix && (inv & imask) == iprefix;
+                digit = (unsigned int)(inv >> shift) & dm;
+            }
         }
+        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, in ? digit : 0xFFFFFFFFu);
+        if (in && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[digit], (unsigned int)__popc(peers));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2048; i += blockDim.x)
@@ -239,6 +252,7 @@ __global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const 
 }
 
 __global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits, int phase, unsigned int *hist) {
+    if (phase == 1 && state[7]) return;
     if (threadIdx.x == 0) {
         const int nb = 1 << bits;
         unsigned long long rem = phase == 0 ? state[2] : state[5];
@@ -254,6 +268,8 @@ __global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits,
             state[0] |= (unsigned long long)d << shift;
             state[1] |= dm << shift;
             state[2] = rem;
+            // after the last value pass hist[d] = number of elements equal to the threshold
+            if (shift == 0) state[7] = (rem == (unsigned long long)hist[d]) ? 1ull : 0ull;
         } else {
             state[3] |= (unsigned long long)d << shift;
             state[4] |= dm << shift;
@@ -266,7 +282,7 @@ __global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits,
 
 __global__ void topk_begin_ties_kernel(unsigned long long *state) {
     // after the value phase state[2] = how many elements equal to the threshold are needed
-    state[3] = 0;
+    state[3] = 0;  // with state[7] set this already means "every tie qualifies"
     state[4] = 0;
     state[5] = state[2];
     state[6] = 0;
