@@ -224,9 +224,9 @@ __global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const 
     const unsigned long long iprefix = state[3], imask = state[4];
     const unsigned int dm = (1u << bits) - 1u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // block-uniform trip count: the warp-wide match below needs converged warps.  Equal
-    // values are the norm here (every unmatched document carries the same fused
-    // probability), so equal digits are aggregated per warp before touching the histogram.
+    // block-uniform trip count: the warp-wide votes below need converged warps.  Runs of
+    // equal values are common here (every unmatched document carries the same fused
+    // probability).
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
         const int64_t i = base + threadIdx.x;
         bool in = false;
@@ -243,8 +243,17 @@ __global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const 
                 digit = (unsigned int)(inv >> shift) & dm;
             }
         }
-        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, in ? digit : 0xFFFFFFFFu);
-        if (in && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[digit], (unsigned int)__popc(peers));
+        // cheap aggregation of the all-equal case (one shuffle + two votes); mixed warps
+        // fall back to per-lane atomics
+        const unsigned int act = __ballot_sync(0xFFFFFFFFu, in);
+        if (act) {
+            const unsigned int d0 = __shfl_sync(0xFFFFFFFFu, digit, __ffs(act) - 1);
+            if (__all_sync(0xFFFFFFFFu, !in || digit == d0)) {
+                if ((int)(__ffs(act) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[d0], (unsigned int)__popc(act));
+            } else if (in) {
+                atomicAdd(&sh[digit], 1u);
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2048; i += blockDim.x)
