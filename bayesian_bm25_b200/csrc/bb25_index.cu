@@ -130,17 +130,13 @@ __global__ void validate_csc_kernel(const float *__restrict__ data, const int32_
     }
     if (bad) atomicOr(flags, bad);
 }
-// ascending check needs column boundaries: one thread per posting looks up whether
-// j is a column start through a boundary bitmap-free trick: compare with previous
-// posting and accept a decrease only where some column starts at j.
+// strictly ascending doc ids inside every column: short columns one thread each ...
 __global__ void validate_sorted_kernel(const int32_t *__restrict__ indices,
                                        const int64_t *__restrict__ indptr, int64_t n_vocab, int *flags) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int bad = 0;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_vocab; t += stride) {
         int64_t s = indptr[t], e = indptr[t + 1];
-        // sample-free full check would be O(df) per thread; do it cooperatively below
-        // for long columns, here only for short ones
         if (e - s <= 64)
             for (int64_t j = s + 1; j < e; j++)
                 if (indices[j] <= indices[j - 1]) bad |= 8;
@@ -150,7 +146,7 @@ __global__ void validate_sorted_kernel(const int32_t *__restrict__ indices,
 __global__ void validate_sorted_long_kernel(const int32_t *__restrict__ indices,
                                             const int64_t *__restrict__ indptr, int64_t n_vocab,
                                             int *flags) {
-    // one block per term, only long columns
+    // ... long columns one block each
     for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
         int64_t s = indptr[t], e = indptr[t + 1];
         if (e - s <= 64) continue;

@@ -67,13 +67,6 @@ struct TileMeta {
     uint8_t m_slot[MAXT];
 };
 
-__device__ __forceinline__ int4 ld_nc_i4(const int4 *p) {
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
 __device__ __forceinline__ float4 ld_nc_f4(const float4 *p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -91,52 +84,6 @@ __device__ __forceinline__ void rmw1(float *acc, uint8_t *cnt, int off, float v)
     }
 }
 
-template <bool COUNT>
-__device__ __forceinline__ void apply4(float *acc, uint8_t *cnt, const int4 &d, const float4 &v,
-                                       int doc_base) {
-    rmw1<COUNT>(acc, cnt, d.x - doc_base, v.x);
-    rmw1<COUNT>(acc, cnt, d.y - doc_base, v.y);
-    rmw1<COUNT>(acc, cnt, d.z - doc_base, v.z);
-    rmw1<COUNT>(acc, cnt, d.w - doc_base, v.w);
-}
-
-// Add postings [s, s+len) of one term into the tile accumulators.  Doc ids inside a
-// posting list are distinct, so no two threads touch the same accumulator.
-template <int NT, bool COUNT>
-__device__ __forceinline__ void scatter_slice(const float *__restrict__ data,
-                                              const int32_t *__restrict__ indices, long long s,
-                                              uint32_t len, float *acc, uint8_t *cnt, int doc_base,
-                                              int tid) {
-    const long long e = s + (long long)len;
-    long long a0 = (s + 3) & ~3ll;  // first 16-byte aligned element
-    if (a0 > e) a0 = e;
-    if (tid < (int)(a0 - s)) {
-        long long j = s + tid;
-        rmw1<COUNT>(acc, cnt, indices[j] - doc_base, data[j]);
-    }
-    const int n4 = (int)((e - a0) >> 2);
-    const int4 *idx4 = reinterpret_cast<const int4 *>(indices + a0);
-    const float4 *val4 = reinterpret_cast<const float4 *>(data + a0);
-    for (int g = tid; g < n4; g += 2 * NT) {
-        int4 d0 = ld_nc_i4(idx4 + g);
-        float4 v0 = ld_nc_f4(val4 + g);
-        const bool two = (g + NT) < n4;
-        int4 d1 = d0;
-        float4 v1 = v0;
-        if (two) {
-            d1 = ld_nc_i4(idx4 + g + NT);
-            v1 = ld_nc_f4(val4 + g + NT);
-        }
-        apply4<COUNT>(acc, cnt, d0, v0, doc_base);
-        if (two) apply4<COUNT>(acc, cnt, d1, v1, doc_base);
-    }
-    const long long t0 = a0 + ((long long)n4 << 2);
-    if (t0 + tid < e) {
-        long long j = t0 + tid;
-        rmw1<COUNT>(acc, cnt, indices[j] - doc_base, data[j]);
-    }
-}
-
 __device__ __forceinline__ int ld_nc_s32(const int32_t *p) {
     int r;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
@@ -148,11 +95,12 @@ __device__ __forceinline__ float ld_nc_f32(const float *p) {
     return r;
 }
 
-// Same contract as scatter_slice, different thread -> posting map: every warp-wide
-// load / accumulator update covers 32 CONSECUTIVE postings (128-byte aligned in the
-// main loop).  Doc ids of a dense posting list are (nearly) consecutive, so the
-// shared-memory read-modify-writes of a warp fall into distinct banks, where the
-// 128-bit-per-lane map above puts lanes 4 documents apart (4-way bank conflicts).
+// Add postings [s, s+len) of one term into the tile accumulators.  Doc ids inside a
+// posting list are distinct, so no two threads touch the same accumulator.  Every
+// warp-wide load / accumulator update covers 32 CONSECUTIVE postings (128-byte aligned
+// in the main loop): doc ids of a dense posting list are (nearly) consecutive, so the
+// shared-memory read-modify-writes of a warp fall into distinct banks (a 128-bit load
+// per lane would put lanes 4 documents apart: 4-way bank conflicts, measured in round 1).
 template <int NT, bool COUNT, int U>
 __device__ __forceinline__ void scatter_slice_s32(const float *__restrict__ data,
                                                   const int32_t *__restrict__ indices, long long s,
@@ -183,19 +131,18 @@ __device__ __forceinline__ void scatter_slice_s32(const float *__restrict__ data
     for (; j < n; j += NT) rmw1<COUNT>(acc, cnt, ld_nc_s32(ip + j) - doc_base, ld_nc_f32(dp + j));
 }
 
-// VAR bit 0: strided 32-bit scatter map (else 128-bit per lane)
-// VAR bit 1: retrieve mode keeps no matched-term counters in the tile; the select
-//            kernel recovers tf for the k winners by searching the posting lists
+// Retrieve mode keeps no matched-term counters in the tile (the select kernel recovers tf
+// for the k winners); the dense-output modes count matched terms per document.
 // resident CTAs per SM the kernel is built for: 5 B/doc of shared memory with counters,
 // 4 B/doc without
-template <int D, int MODE, int VAR>
+template <int D, int MODE>
 constexpr int ctas_per_sm() {
-    return D > 16384 ? 1 : (D > 8192 ? 1 : 2) * (((MODE == MODE_RETRIEVE) && (VAR & 2)) ? 3 : 2);
+    return D > 16384 ? 1 : (D > 8192 ? 1 : 2) * ((MODE == MODE_RETRIEVE) ? 3 : 2);
 }
 
-template <int D, int NT, int MODE, int VAR>
-__global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE, VAR>()) tile_kernel(const __grid_constant__ TileArgs a) {
-    constexpr bool HAS_CNT = (MODE != MODE_RETRIEVE) || !(VAR & 2);
+template <int D, int NT, int MODE>
+__global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE>()) tile_kernel(const __grid_constant__ TileArgs a) {
+    constexpr bool HAS_CNT = (MODE != MODE_RETRIEVE);
     extern __shared__ __align__(16) unsigned char smem[];
     float *acc = reinterpret_cast<float *>(smem);
     uint8_t *cnt = smem + (size_t)D * 4;
@@ -262,13 +209,8 @@ __global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE, VAR>()) tile_kernel(c
                 const int flags = meta->m_flags[i];
                 if (len) {
                     const bool count = HAS_CNT && !(flags & 1);
-                    if (VAR & 1) {
-                        if (count) scatter_slice_s32<NT, true, 4>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
-                        else scatter_slice_s32<NT, false, 4>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
-                    } else {
-                        if (count) scatter_slice<NT, true>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
-                        else scatter_slice<NT, false>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
-                    }
+                    if (count) scatter_slice_s32<NT, true, 4>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
+                    else scatter_slice_s32<NT, false, 4>(a.data, a.indices, s, len, acc, cnt, doc_base, tid);
                 }
                 __syncthreads();
                 if (flags & 2) {
@@ -1232,26 +1174,14 @@ __global__ void fill_strided_f64_kernel(double *out, int64_t n, int64_t stride, 
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
-// kernel variant (see tile_kernel): BB25_VARIANT=0..3 overrides the default for A/B runs
-static int kernel_variant() {
-    const char *e = getenv("BB25_VARIANT");
-    return (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : 3;
-}
-
-template <int DV, int NTV, int MODE, int VAR>
+template <int DV, int NTV, int MODE>
 static int launch_tile_inst(const bb25_index *idx, const TileArgs &a, long long n_items, cudaStream_t st) {
-    constexpr bool has_cnt = (MODE != MODE_RETRIEVE) || !(VAR & 2);
+    constexpr bool has_cnt = (MODE != MODE_RETRIEVE);
     const size_t smem = (size_t)DV * (has_cnt ? 5 : 4) + sizeof(TileMeta);
-    BB25_CUDA(cudaFuncSetAttribute(tile_kernel<DV, NTV, MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    int per_sm = ctas_per_sm<DV, MODE, VAR>();
-    if (const char *e = getenv("BB25_CTAS_PER_SM")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= per_sm) per_sm = v;
-    }
-    long long grid = (long long)idx->sm_count * per_sm;
+    BB25_CUDA(cudaFuncSetAttribute(tile_kernel<DV, NTV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (long long)idx->sm_count * ctas_per_sm<DV, MODE>();
     if (grid > n_items) grid = n_items;
-    tile_kernel<DV, NTV, MODE, VAR><<<(unsigned)grid, NTV, smem, st>>>(a);
+    tile_kernel<DV, NTV, MODE><<<(unsigned)grid, NTV, smem, st>>>(a);
     BB25_LAUNCH_CHECK();
     return 0;
 }
@@ -1262,21 +1192,12 @@ static int launch_tile(const bb25_index *idx, const TileArgs &a, cudaStream_t st
     const long long n_items = (long long)(a.tile_end - a.tile_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-    const int var = kernel_variant();
-#define BB25_TILE_CASE(DV, NTV)                                                        \
-    switch (var) {                                                                     \
-    case 0: return launch_tile_inst<DV, NTV, MODE, 0>(idx, a, n_items, st);            \
-    case 1: return launch_tile_inst<DV, NTV, MODE, 1>(idx, a, n_items, st);            \
-    case 2: return launch_tile_inst<DV, NTV, MODE, 2>(idx, a, n_items, st);            \
-    default: return launch_tile_inst<DV, NTV, MODE, 3>(idx, a, n_items, st);           \
-    }
     switch (idx->tile_docs) {
-    case 8192: BB25_TILE_CASE(8192, 256)
-    case 16384: BB25_TILE_CASE(16384, 512)
-    case 32768: BB25_TILE_CASE(32768, 1024)
+    case 8192: return launch_tile_inst<8192, 256, MODE>(idx, a, n_items, st);
+    case 16384: return launch_tile_inst<16384, 512, MODE>(idx, a, n_items, st);
+    case 32768: return launch_tile_inst<32768, 1024, MODE>(idx, a, n_items, st);
     default: set_error("unsupported tile size %d", idx->tile_docs); return 1;
     }
-#undef BB25_TILE_CASE
 }
 
 static void base_args(const bb25_index *idx, TileArgs &a) {
@@ -1504,7 +1425,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.out_scores = out_scores;
     sa.out_probs = out_probs;
     sa.n_cand_total = d_ncand;
-    sa.tf_search = (blockk || (kernel_variant() & 2)) ? 1 : 0;  // keys carry no tf in those kernels
+    sa.tf_search = 1;  // candidate keys carry no matched-term count
     sa.indices = idx->indices;
     sa.indptr = idx->indptr;
     sa.blk_tab = idx->blk_tab;
