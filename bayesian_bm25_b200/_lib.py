@@ -54,6 +54,8 @@ SIGNATURES = {
     "bb25_retrieve_route_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_retrieve_timing": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "bb25_merge_topk": (_i32, [_i32, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bb25_pack_topk": (_i32, [_i32, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "bb25_merge_topk_packed": (_i32, [_i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bb25_topk_f64": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "bb25_sigmoid": (_i32, [_i32, _vp, _i64, _vp, _vp]),
     "bb25_logit": (_i32, [_i32, _vp, _i64, _vp, _vp]),

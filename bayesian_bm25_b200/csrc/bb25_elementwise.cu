@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(256) blockmax_csc_kernel(const float *__restri
 // One CTA per query: the S*k (score, global id) keys are loaded into shared memory, the
 // k-th largest is found by radix select, the k winners are compacted with their source
 // positions and sorted (k elements instead of S*k).
-template <int NT>
+// PACKED: the lists arrive as 16-byte entries {merge key, fp64 probability bits} (one
+// all-gather instead of three, 16 instead of 20 bytes per entry); `ids` then points to them.
+template <int NT, bool PACKED>
 __global__ void __launch_bounds__(NT) merge_kernel(const int64_t *__restrict__ ids,
                                                    const float *__restrict__ scores,
                                                    const double *__restrict__ probs, int S, int64_t Q,
@@ -162,8 +164,9 @@ __global__ void __launch_bounds__(NT) merge_kernel(const int64_t *__restrict__ i
         const int s = i / k, r = i % k;
         const int64_t o = ((int64_t)s * Q + q) * k + r;
         // (score desc, global id asc); ids < 2^32
-        keys[i] = ((unsigned long long)__float_as_uint(scores[o]) << 32) |
-                  (unsigned long long)(0xFFFFFFFFu - (uint32_t)ids[o]);
+        keys[i] = PACKED ? (unsigned long long)ids[2 * o]
+                         : (((unsigned long long)__float_as_uint(scores[o]) << 32) |
+                            (unsigned long long)(0xFFFFFFFFu - (uint32_t)ids[o]));
     }
     for (int i = tid; i < kpad; i += NT) {
         top[i] = 0ull;
@@ -205,9 +208,28 @@ __global__ void __launch_bounds__(NT) merge_kernel(const int64_t *__restrict__ i
         const unsigned int i = tsrc[r];
         const int s = i / k, rr = i % k;
         const int64_t o = ((int64_t)s * Q + q) * k + rr;
-        out_ids[q * k + r] = ids[o];
-        if (out_scores) out_scores[q * k + r] = scores[o];
-        out_probs[q * k + r] = probs[o];
+        if (PACKED) {
+            const unsigned long long key = top[r];
+            out_ids[q * k + r] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+            if (out_scores) out_scores[q * k + r] = __uint_as_float((uint32_t)(key >> 32));
+            out_probs[q * k + r] = __longlong_as_double((long long)ids[2 * o + 1]);
+        } else {
+            out_ids[q * k + r] = ids[o];
+            if (out_scores) out_scores[q * k + r] = scores[o];
+            out_probs[q * k + r] = probs[o];
+        }
+    }
+}
+
+// (ids, scores, probs) -> 16-byte entries {(score bits << 32) | (2^32-1 - id), probability bits}
+__global__ void __launch_bounds__(256) pack_topk_kernel(const int64_t *__restrict__ ids, const float *__restrict__ scores,
+                                                        const double *__restrict__ probs, int64_t n,
+                                                        int64_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        out[2 * i] = (int64_t)(((unsigned long long)__float_as_uint(scores[i]) << 32) |
+                               (unsigned long long)(0xFFFFFFFFu - (uint32_t)ids[i]));
+        out[2 * i + 1] = __double_as_longlong(probs[i]);
     }
 }
 
@@ -498,9 +520,41 @@ int bb25_merge_topk(int device, const int64_t *ids, const float *scores, const d
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
     const size_t smem = (size_t)n_shards * k * 8 + (size_t)kpad * 12 + 260 * 4;
-    BB25_CUDA(cudaFuncSetAttribute(merge_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_kernel<512><<<(unsigned)n_queries, 512, smem, (cudaStream_t)stream>>>(ids, scores, probs, n_shards, n_queries, k,
-                                                                               kpad, out_ids, out_scores, out_probs);
+    BB25_CUDA(cudaFuncSetAttribute(merge_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<512, false><<<(unsigned)n_queries, 512, smem, (cudaStream_t)stream>>>(ids, scores, probs, n_shards, n_queries,
+                                                                                      k, kpad, out_ids, out_scores, out_probs);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_pack_topk(int device, const int64_t *ids, const float *scores, const double *probs, int64_t n,
+                   int64_t *out_packed, void *stream) {
+    if (n < 0 || !out_packed || (n > 0 && (!ids || !scores || !probs))) { set_error("bad pack arguments"); return 1; }
+    if (n == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_topk_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, scores, probs, n, out_packed);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
+int bb25_merge_topk_packed(int device, const int64_t *packed, int n_shards, int64_t n_queries, int k,
+                           int64_t *out_ids, float *out_scores, double *out_probs, void *stream) {
+    if (n_shards < 1 || n_queries < 0 || k < 1 || !packed || !out_ids || !out_probs) { set_error("bad merge arguments"); return 1; }
+    if ((int64_t)n_shards * k > 16384) { set_error("n_shards * k must be <= 16384"); return 1; }
+    if (n_queries == 0) return 0;
+    if (bb25_device_count() < 1) { set_error("no CUDA device available (libbb25 has no CPU fallback)"); return 1; }
+    DeviceGuard dg(device);
+    if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
+    int kpad = 2;
+    while (kpad < k) kpad <<= 1;
+    const size_t smem = (size_t)n_shards * k * 8 + (size_t)kpad * 12 + 260 * 4;
+    BB25_CUDA(cudaFuncSetAttribute(merge_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<512, true><<<(unsigned)n_queries, 512, smem, (cudaStream_t)stream>>>(packed, nullptr, nullptr, n_shards, n_queries,
+                                                                                     k, kpad, out_ids, out_scores, out_probs);
     BB25_LAUNCH_CHECK();
     return 0;
 }

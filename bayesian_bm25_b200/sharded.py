@@ -48,6 +48,26 @@ def merge_topk_device(ids: torch.Tensor, scores: torch.Tensor, probs: torch.Tens
     return out_ids, out_sc, out_pr
 
 
+def pack_topk_device(ids: torch.Tensor, scores: torch.Tensor, probs: torch.Tensor) -> torch.Tensor:
+    """[Q,k] x3 -> [Q,k,2] int64 entries {merge key, probability bits} (global ids < 2^32)."""
+    out = torch.empty(tuple(ids.shape) + (2,), dtype=torch.int64, device=ids.device)
+    _lib.check(_lib.lib().bb25_pack_topk(ids.device.index, ids.contiguous().data_ptr(), scores.contiguous().data_ptr(),
+                                         probs.contiguous().data_ptr(), ids.numel(), out.data_ptr(), _lib.stream_ptr()))
+    return out
+
+
+def merge_packed_device(packed: torch.Tensor):
+    """[S,Q,k,2] int64 -> merged (ids int64, scores fp32, probs fp64) [Q,k]."""
+    s, q, k, _ = packed.shape
+    out_ids = torch.empty((q, k), dtype=torch.int64, device=packed.device)
+    out_sc = torch.empty((q, k), dtype=torch.float32, device=packed.device)
+    out_pr = torch.empty((q, k), dtype=torch.float64, device=packed.device)
+    _lib.check(_lib.lib().bb25_merge_topk_packed(packed.device.index, packed.contiguous().data_ptr(), s, q, k,
+                                                 out_ids.data_ptr(), out_sc.data_ptr(), out_pr.data_ptr(),
+                                                 _lib.stream_ptr()))
+    return out_ids, out_sc, out_pr
+
+
 class ShardedRetriever:
     """Wraps a rank-local BayesianBM25Scorer (indexed on this rank's shard).
 
@@ -77,8 +97,12 @@ class ShardedRetriever:
             self._stats = {k: self._stats.get(k, 0) + v for k, v in st.items()}
 
     def _exchange(self, ids, sc, pr):
-        g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
-        return merge_topk_device(g_ids, g_sc, g_pr)
+        # one collective: 16-byte packed entries, gathered rank-major, merged on every rank
+        packed = pack_topk_device(ids, sc, pr)
+        world = dist.get_world_size(self.group)
+        buf = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(buf, packed, group=self.group)
+        return merge_packed_device(buf.view((world,) + tuple(packed.shape)))
 
     def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
         sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -96,10 +120,14 @@ class ShardedRetriever:
             self._add_stats(reset=True)
             if ev:
                 ev[1].record()
-            g_ids, g_sc, g_pr = allgather_topk(ids, sc, pr, self.group)
+            packed = pack_topk_device(ids, sc, pr)
+            world = dist.get_world_size(self.group)
+            buf = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype,
+                              device=packed.device)
+            dist.all_gather_into_tensor(buf, packed, group=self.group)
             if ev:
                 ev[2].record()
-            out = merge_topk_device(g_ids, g_sc, g_pr)
+            out = merge_packed_device(buf.view((world,) + tuple(packed.shape)))
             if ev:
                 ev[3].record()
                 ev[3].synchronize()

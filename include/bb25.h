@@ -156,6 +156,15 @@ int bb25_merge_topk(int device, const int64_t *ids, const float *scores, const d
                     int n_shards, int64_t n_queries, int k, int64_t *out_ids, float *out_scores,
                     double *out_probs, void *stream);
 
+/* The same merge for lists packed as 16-byte entries {(fp32 score bits << 32) | (2^32-1 - id),
+ * fp64 probability bits}: ONE all-gather of [Q,k,2] int64 per rank instead of three tensors.
+ * bb25_pack_topk builds the entries from a shard's (ids, scores, probs). */
+int bb25_pack_topk(int device, const int64_t *ids, const float *scores, const double *probs, int64_t n,
+                   int64_t *out_packed /*dev [n][2]*/, void *stream);
+int bb25_merge_topk_packed(int device, const int64_t *packed /*dev [S][Q][k][2]*/, int n_shards,
+                           int64_t n_queries, int k, int64_t *out_ids, float *out_scores,
+                           double *out_probs, void *stream);
+
 /* top-k of a dense fp64 vector (values >= 0), (value desc, index asc):
  * MultiFieldScorer.retrieve's argsort (multi_field.py:199) made deterministic. */
 int bb25_topk_f64(int device, const double *vals /*dev [n]*/, int64_t n, int k,

@@ -353,6 +353,11 @@ def test_merge_topk_vs_oracle():
         got = sharded.merge_topk_device(torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda(), torch.from_numpy(pr).cuda())
         for g_, w_ in zip(got, want):
             np.testing.assert_array_equal(g_.cpu().numpy(), w_)
+        # packed form (what the sharded retriever all-gathers)
+        packed = torch.stack([sharded.pack_topk_device(torch.from_numpy(ids[s_]).cuda(), torch.from_numpy(sc[s_]).cuda(),
+                                                       torch.from_numpy(pr[s_]).cuda()) for s_ in range(S)])
+        for g_, w_ in zip(sharded.merge_packed_device(packed), want):
+            np.testing.assert_array_equal(g_.cpu().numpy(), w_)
 
 
 def test_topk_f64_vs_oracle():
