@@ -180,7 +180,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--prune-level", type=int, default=3, help="pruning level of the extra 'pruned' pass")
-    ap.add_argument("--shard-chunks", type=int, default=2, help="query sub-batches pipelined against the all-gather (N>1)")
+    ap.add_argument("--shard-chunks", type=int, default=1,
+                    help="query sub-batches pipelined against the all-gather (N>1); 1 measured best at Q=10k (profiles/r01)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
