@@ -311,6 +311,11 @@ __global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits,
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
 }
 
+__global__ void topk_init_kernel(unsigned long long *state, unsigned int *hist, int k) {
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0u;
+    if (threadIdx.x < 8) state[threadIdx.x] = threadIdx.x == 2 ? (unsigned long long)k : 0ull;
+}
+
 __global__ void topk_begin_ties_kernel(unsigned long long *state) {
     // after the value phase state[2] = how many elements equal to the threshold are needed
     state[3] = 0;  // with state[7] set this already means "every tie qualifies"
@@ -577,10 +582,8 @@ int bb25_topk_f64(int device, const double *vals, int64_t n, int k, int64_t *out
     unsigned long long *cb = (unsigned long long *)(ws + o_cb), *ci = (unsigned long long *)(ws + o_ci);
     int rc = 1;
     do {
-        unsigned long long h_state[8] = {0, 0, (unsigned long long)k, 0, 0, 0, 0, 0};
-        if (cudaMemsetAsync(ws, 0, o_cb, st) != cudaSuccess) break;
-        if (cudaMemcpyAsync(state, h_state, sizeof(h_state), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-        if (cudaStreamSynchronize(st) != cudaSuccess) break;  // h_state is on the stack
+        topk_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
+        count_launch();
         int64_t blocks = (n + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
         // value phase: 64 bits as 11,11,11,11,11,9

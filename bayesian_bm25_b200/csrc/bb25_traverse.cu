@@ -1219,6 +1219,19 @@ __global__ void fuse_const_kernel(double *acc, int64_t n, double p, FuseSpec f) 
     if (i < n) acc[i] = fuse_step(acc[i], d_logit(p), f);
 }
 
+// a short query passed by value: no host->device copy, no stream synchronisation
+struct InlineQuery {
+    int n;
+    int32_t t[64];
+};
+__global__ void stage_query_kernel(const InlineQuery iq, int32_t *d_src, int64_t *d_qoff) {
+    if (threadIdx.x < iq.n) d_src[threadIdx.x] = iq.t[threadIdx.x];
+    if (threadIdx.x == 0) {
+        d_qoff[0] = 0;
+        d_qoff[1] = iq.n;
+    }
+}
+
 static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const int32_t *q_terms_host,
                      int n_terms, float *out_scores, double *out_probs, int64_t out_stride,
                      cudaStream_t st, const FuseSpec *fuse = nullptr) {
@@ -1260,10 +1273,18 @@ static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const
     int64_t *d_qoff = (int64_t *)(ws + o_qoff);
     int32_t *d_src = (int32_t *)(ws + o_src);
     int *d_err = (int *)(ws + o_err);
-    int64_t hq[2] = {0, n_terms};
-    BB25_CUDA(cudaMemcpyAsync(d_src, q_terms_host, sizeof(int32_t) * (size_t)n_terms, cudaMemcpyHostToDevice, st));
-    BB25_CUDA(cudaMemcpyAsync(d_qoff, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
-    BB25_CUDA(cudaStreamSynchronize(st));  // hq / q_terms_host are pageable stack/user memory
+    if (n_terms <= 64) {
+        InlineQuery iq;
+        iq.n = n_terms;
+        for (int i = 0; i < n_terms; i++) iq.t[i] = q_terms_host[i];
+        stage_query_kernel<<<1, 64, 0, st>>>(iq, d_src, d_qoff);
+        BB25_LAUNCH_CHECK();
+    } else {
+        int64_t hq[2] = {0, n_terms};
+        BB25_CUDA(cudaMemcpyAsync(d_src, q_terms_host, sizeof(int32_t) * (size_t)n_terms, cudaMemcpyHostToDevice, st));
+        BB25_CUDA(cudaMemcpyAsync(d_qoff, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
+        BB25_CUDA(cudaStreamSynchronize(st));  // hq / q_terms_host are pageable stack/user memory
+    }
     BB25_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
     prep_queries_kernel<<<1, 32, 0, st>>>(d_src, d_qoff, 1, 0, idx->n_vocab, nullptr, d_terms, d_nc, nullptr, nullptr, nullptr, d_err);
     BB25_LAUNCH_CHECK();

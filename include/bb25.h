@@ -19,7 +19,9 @@
  *  - There is no CPU fallback: without a usable CUDA device every compute call
  *    fails with an error.
  *  - An index handle is immutable after creation; query calls on ONE handle
- *    are serialised internally (they share a device workspace).
+ *    are serialised internally on the host and share a device workspace, so
+ *    concurrent calls on one handle must use the same stream (the single-query
+ *    calls are asynchronous: they return once the work is enqueued).
  *  - Doc ids are int64 in the interface; one index (= one shard) holds at most
  *    2^29 documents.  Scores are fp32, probabilities fp64, as in the reference.
  */
