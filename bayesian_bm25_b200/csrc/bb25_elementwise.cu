@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(256) pack_topk_kernel(const int64_t *__restric
 __global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const unsigned long long *state,
                                  int shift, int bits, int phase, unsigned int *hist) {
     __shared__ unsigned int sh[2048];
+    if (state[8]) return;                // the seeded fast path already produced the result
     if (phase == 1 && state[7]) return;  // every tie on the threshold value is taken: nothing to select
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -283,6 +284,7 @@ __global__ void topk_hist_kernel(const double *__restrict__ v, int64_t n, const 
 }
 
 __global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits, int phase, unsigned int *hist) {
+    if (state[8]) return;
     if (phase == 1 && state[7]) return;
     if (threadIdx.x == 0) {
         const int nb = 1 << bits;
@@ -311,12 +313,116 @@ __global__ void topk_scan_kernel(unsigned long long *state, int shift, int bits,
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
 }
 
+// state words: [0..7] radix select (see above), [8] done flag, [9] seed threshold, [10] seeded-collect counter
 __global__ void topk_init_kernel(unsigned long long *state, unsigned int *hist, int k) {
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0u;
-    if (threadIdx.x < 8) state[threadIdx.x] = threadIdx.x == 2 ? (unsigned long long)k : 0ull;
+    if (threadIdx.x < 16) state[threadIdx.x] = threadIdx.x == 2 ? (unsigned long long)k : 0ull;
+}
+
+// ---- seeded fast path for k <= number of strips -----------------------------------------
+// The maxima of G disjoint strips are G distinct elements, so the k-th largest strip maximum
+// is a valid lower bound of the k-th largest element.  Two scans (strip maxima, collect >=
+// seed) and one small sort replace the 12 radix passes whenever the collected set fits.
+constexpr int kTopkStrips = 148 * 8;
+constexpr int kTopkCollectCap = 8192;
+
+__global__ void __launch_bounds__(256) topk_strip_max_kernel(const double *__restrict__ v, int64_t n,
+                                                             unsigned long long *__restrict__ strip_max) {
+    __shared__ unsigned long long sm[8];
+    const int64_t len = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * len, hi = lo + len < n ? lo + len : n;
+    unsigned long long m = 0ull;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, m, d);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) m = sm[w] > m ? sm[w] : m;
+        strip_max[blockIdx.x] = m;
+    }
+}
+
+__global__ void __launch_bounds__(1024) topk_seed_kernel(const unsigned long long *__restrict__ strip_max, int n_strips,
+                                                         int k, unsigned long long *state) {
+    __shared__ unsigned long long s[2048];
+    for (int i = threadIdx.x; i < 2048; i += 1024) s[i] = i < n_strips ? strip_max[i] : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= 2048; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int t = threadIdx.x;
+            const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+            const bool desc = (lo & size) == 0;
+            const unsigned long long x = s[lo], y = s[hi];
+            if ((x < y) == desc) { s[lo] = y; s[hi] = x; }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) state[9] = s[k - 1];
+}
+
+__global__ void __launch_bounds__(256) topk_collect_seeded_kernel(const double *__restrict__ v, int64_t n,
+                                                                  unsigned long long *state,
+                                                                  unsigned long long *cb, unsigned long long *ci) {
+    const unsigned long long seed = state[9];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+        if (b >= seed) {
+            const unsigned long long pos = atomicAdd(&state[10], 1ull);
+            if (pos < (unsigned long long)kTopkCollectCap) {
+                cb[pos] = b;
+                ci[pos] = 0xFFFFFFFFFFFFFFFFull - (unsigned long long)i;
+            }
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) topk_seeded_final_kernel(unsigned long long *state, const unsigned long long *cb,
+                                                               const unsigned long long *ci, int k,
+                                                               int64_t *out_ids, double *out_vals) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const unsigned long long cnt = state[10];
+    if (cnt > (unsigned long long)kTopkCollectCap || cnt < (unsigned long long)k) return;  // radix path takes over
+    int P = 2;
+    while (P < (int)cnt) P <<= 1;
+    unsigned long long *kb = reinterpret_cast<unsigned long long *>(smem);
+    unsigned long long *ki = kb + P;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P; i += NT) {
+        kb[i] = i < (int)cnt ? cb[i] : 0ull;
+        ki[i] = i < (int)cnt ? ci[i] : 0ull;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (P >> 1); t += NT) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long xb = kb[lo], yb = kb[hi], xi = ki[lo], yi = ki[hi];
+                const bool less = xb < yb || (xb == yb && xi < yi);
+                if (less == desc) {
+                    kb[lo] = yb; kb[hi] = xb;
+                    ki[lo] = yi; ki[hi] = xi;
+                }
+            }
+            __syncthreads();
+        }
+    for (int r = tid; r < k; r += NT) {
+        out_ids[r] = (int64_t)(0xFFFFFFFFFFFFFFFFull - ki[r]);
+        out_vals[r] = __longlong_as_double((long long)kb[r]);
+    }
+    if (tid == 0) state[8] = 1ull;
 }
 
 __global__ void topk_begin_ties_kernel(unsigned long long *state) {
+    if (state[8]) return;
     // after the value phase state[2] = how many elements equal to the threshold are needed
     state[3] = 0;  // with state[7] set this already means "every tie qualifies"
     state[4] = 0;
@@ -327,6 +433,7 @@ __global__ void topk_begin_ties_kernel(unsigned long long *state) {
 // gather the k winners (unordered) as (value bits, ~index) pairs
 __global__ void topk_collect_kernel(const double *__restrict__ v, int64_t n, unsigned long long *state, int k,
                                     unsigned long long *cand_bits, unsigned long long *cand_inv) {
+    if (state[8]) return;
     const unsigned long long thr = state[0];
     const unsigned long long ithr = state[3];  // smallest admissible ~index among ties
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -344,10 +451,12 @@ __global__ void topk_collect_kernel(const double *__restrict__ v, int64_t n, uns
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) topk_sort_kernel(const unsigned long long *cand_bits,
+__global__ void __launch_bounds__(NT) topk_sort_kernel(const unsigned long long *state,
+                                                       const unsigned long long *cand_bits,
                                                        const unsigned long long *cand_inv, int k, int P,
                                                        int64_t *out_ids, double *out_vals) {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (state[8]) return;
     unsigned long long *kb = reinterpret_cast<unsigned long long *>(smem);
     unsigned long long *ki = kb + P;
     const int tid = threadIdx.x;
@@ -575,17 +684,31 @@ int bb25_topk_f64(int device, const double *vals, int64_t n, int k, int64_t *out
     if (!dg.ok) { set_error("cannot select CUDA device %d", device); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char *ws = nullptr;
-    const size_t o_hist = 64, o_cb = o_hist + 2048 * 4, o_ci = o_cb + (size_t)k * 8;
-    BB25_CUDA(cudaMallocAsync(&ws, o_ci + (size_t)k * 8, st));
+    const size_t o_hist = 128, o_cb = o_hist + 2048 * 4, o_ci = o_cb + (size_t)k * 8;
+    const size_t o_sm = o_ci + (size_t)k * 8, o_cb2 = o_sm + (size_t)kTopkStrips * 8;
+    const size_t o_ci2 = o_cb2 + (size_t)kTopkCollectCap * 8;
+    BB25_CUDA(cudaMallocAsync(&ws, o_ci2 + (size_t)kTopkCollectCap * 8, st));
     unsigned long long *state = (unsigned long long *)ws;
     unsigned int *hist = (unsigned int *)(ws + o_hist);
     unsigned long long *cb = (unsigned long long *)(ws + o_cb), *ci = (unsigned long long *)(ws + o_ci);
+    unsigned long long *strip_max = (unsigned long long *)(ws + o_sm);
+    unsigned long long *cb2 = (unsigned long long *)(ws + o_cb2), *ci2 = (unsigned long long *)(ws + o_ci2);
     int rc = 1;
     do {
         topk_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
         count_launch();
         int64_t blocks = (n + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
+        if (k <= kTopkStrips && n >= (int64_t)kTopkStrips * 64) {
+            // seeded fast path; on overflow (massive ties) it leaves state[8] == 0 and the radix
+            // passes below do the work, otherwise they return at once
+            topk_strip_max_kernel<<<kTopkStrips, 256, 0, st>>>(vals, n, strip_max);
+            topk_seed_kernel<<<1, 1024, 0, st>>>(strip_max, kTopkStrips, k, state);
+            topk_collect_seeded_kernel<<<(unsigned)blocks, 256, 0, st>>>(vals, n, state, cb2, ci2);
+            if (cudaFuncSetAttribute(topk_seeded_final_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTopkCollectCap * 16) != cudaSuccess) break;
+            topk_seeded_final_kernel<512><<<1, 512, (size_t)kTopkCollectCap * 16, st>>>(state, cb2, ci2, k, out_ids, out_vals);
+            count_launch(4);
+        }
         // value phase: 64 bits as 11,11,11,11,11,9
         const int vshift[6] = {53, 42, 31, 20, 9, 0}, vbits[6] = {11, 11, 11, 11, 11, 9};
         for (int p = 0; p < 6; p++) {
@@ -606,7 +729,7 @@ int bb25_topk_f64(int device, const double *vals, int64_t n, int k, int64_t *out
         int P = 2;
         while (P < k) P <<= 1;
         if (cudaFuncSetAttribute(topk_sort_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16) != cudaSuccess) break;
-        topk_sort_kernel<512><<<1, 512, (size_t)P * 16, st>>>(cb, ci, k, P, out_ids, out_vals);
+        topk_sort_kernel<512><<<1, 512, (size_t)P * 16, st>>>(state, cb, ci, k, P, out_ids, out_vals);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) break;
         rc = 0;
