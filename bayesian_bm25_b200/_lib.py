@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbb25.so")
+SO_PATH = os.environ.get("BB25_LIB") or os.path.join(_HERE, "libbb25.so")  # BB25_LIB: tuning builds only
 
 GATING = {"none": 0, "relu": 1, "swish": 2, "gelu": 3, "softplus": 4}
 

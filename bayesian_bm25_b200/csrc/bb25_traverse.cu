@@ -531,7 +531,10 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
 // latency.  Items are block-major, so the whole chip works on a handful of adjacent
 // blocks whose index slices sit in L2.
 // =================================================================================
-constexpr int QC = 16;       // queries per warp work item
+#ifndef BB25_QC
+#define BB25_QC 8
+#endif
+constexpr int QC = BB25_QC;  // queries per warp work item
 constexpr int BK_WARPS = 8;  // warps per CTA (6 CTAs/SM -> 48 warps, 192 KB of accumulators)
 
 struct BlockArgs {
@@ -614,7 +617,10 @@ __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, con
 // row: 128-bit row loads and 128-bit shared read-modify-writes, 4 documents per lane per
 // step, instead of walking ~1000 (doc id, value) postings.  Absent documents hold -0.0f,
 // and x + (-0.0f) == x, so the sums stay bit-exact.
-constexpr int kDenseAddMinLen = 512;
+#ifndef BB25_DENSE_MIN
+#define BB25_DENSE_MIN 320
+#endif
+constexpr int kDenseAddMinLen = BB25_DENSE_MIN;
 template <bool FRESH = false>
 __device__ __forceinline__ void dense_add_warp(const float *__restrict__ row, float4 *acc4, int lane) {
     const float4 *r4 = reinterpret_cast<const float4 *>(row);
