@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
 
 // =================================================================================
 // Warp-private traversal (retrieve mode).  A BLOCK = 1024 consecutive documents whose
-// fp32 accumulators (4 KB) belong to ONE warp; a warp pulls (block, 16-query chunk)
+// fp32 accumulators (4 KB) belong to ONE warp; a warp pulls (block, 8-query chunk)
 // items from a global counter and, for every query of the chunk,
 //   1. reads the block-table entries of the query's terms (offset, length, block max),
 //   2. forms the block's score upper bound in query order and SKIPS the unit when the
