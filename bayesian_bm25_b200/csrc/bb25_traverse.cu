@@ -884,8 +884,11 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
             unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
             for (int w = lane; w < kBlockDocs / 4; w += 32) {
                 const float4 v = acc4[w];
-                if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+                // sums are >= +0: the quad's maximum decides both "untouched" and "can any qualify"
+                const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                if (mx == 0.f) continue;
                 acc4[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (__float_as_uint(mx) < thr_score) continue;
                 const float av[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
