@@ -195,7 +195,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from bayesian_bm25_b200 import BayesianBM25Scorer, _lib, index_build, sharded, synthetic
+    from bayesian_bm25_b200 import BayesianBM25Scorer, _lib, sharded, synthetic
 
     world = _env_int("WORLD_SIZE", 1)
     rank = _env_int("RANK", 0)

@@ -3,7 +3,6 @@ committed golden vectors.  Bars (BASELINE.json north_star): top-k ids bit-exact 
 ties by doc id, fp32 scores bit-exact (<= 1e-5 rel allowed), probabilities within
 1e-6 absolute -- asserted here at PROB_TOL = 1e-9."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest
@@ -12,9 +11,6 @@ import torch
 pytestmark = pytest.mark.gpu
 
 PROB_TOL = 1e-9
-
-from bb25_testutil import case_scores  # noqa: E402
-
 
 def _pkg():
     import bayesian_bm25_b200 as pkg

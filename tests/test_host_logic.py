@@ -2,7 +2,6 @@
 restatement, estimators vs the reference's numbers, the C ABI surface, synthetic
 generators and document-range sharding."""
 import ctypes
-import json
 import os
 import re
 
