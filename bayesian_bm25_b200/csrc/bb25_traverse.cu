@@ -553,7 +553,8 @@ struct BlockArgs {
     unsigned int *cand_cnt;
     unsigned long long *cand_key;
     int cap;
-    int prune;  // 0 exhaustive, 1 block-max skip, 2 block-max skip + MaxScore units
+    int split;  // 1: split evaluation (register sums for documents matching frequent terms only)
+    int prune;  // 0 exhaustive, 1 block-max skip, 2 + dense-pass skip by the frequent terms' bound
     const int32_t *dense_slot;
     const float *dense_vals;
     int64_t dense_stride;
@@ -681,6 +682,15 @@ __device__ __forceinline__ void emit_if_candidate(float v, uint32_t local_id, ui
     }
 }
 
+// rare path of the register epilogue, kept out of line so it does not cost registers
+__device__ __noinline__ void emit_quad(float4 v, uint32_t first_id, uint32_t thr_score, unsigned long long thr,
+                                       unsigned int *ccnt, unsigned long long *crow, int cap) {
+    emit_if_candidate(v.x, first_id + 0, thr_score, thr, ccnt, crow, cap);
+    emit_if_candidate(v.y, first_id + 1, thr_score, thr, ccnt, crow, cap);
+    emit_if_candidate(v.z, first_id + 2, thr_score, thr, ccnt, crow, cap);
+    emit_if_candidate(v.w, first_id + 3, thr_score, thr, ccnt, crow, cap);
+}
+
 template <int WARPS, bool MS>
 __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -741,97 +751,116 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                     continue;
                 }
                 const int dslot = (a.dense_vals && lane < m && e.len > 0) ? a.dense_slot[e.term] : -1;
-                if (MS && a.prune >= 2 && thr_score != 0u) {
-                    // ---- MaxScore split of the query's terms for this block -------------------
-                    // NE ("non-essential"): head terms with a dense value row whose block maxima,
-                    // summed, stay below the threshold: a document holding only NE terms cannot
-                    // qualify.  Everything else (S) is scattered as usual; NE values are then
-                    // GATHERED only for documents some S term touched.  The NE bound is summed in
-                    // ascending order with a 1e-5 relative margin, which dominates the rounding
-                    // difference to any other summation order (m <= 32 terms).
-                    const float thr_val = __uint_as_float(thr_score);
-                    unsigned rem = __ballot_sync(0xFFFFFFFFu, dslot >= 0);
-                    unsigned ne_mask = 0u;
-                    float run = 0.f;
-                    while (rem) {
-                        float best = 0.f;
-                        int bl = -1;
-                        for (unsigned mm = rem; mm; mm &= mm - 1) {
-                            const int L = __ffs(mm) - 1;
-                            const float v = __shfl_sync(0xFFFFFFFFu, e.bmax, L);
-                            if (bl < 0 || v < best) { best = v; bl = L; }
-                        }
-                        const float cand = __fadd_rn(run, best);
-                        if (!(__fmul_rn(cand, 1.00001f) < thr_val)) break;
-                        run = cand;
-                        ne_mask |= 1u << bl;
-                        rem &= ~(1u << bl);
-                    }
+                if (MS && a.split) {
+                    // ---- split evaluation of the unit ------------------------------------------
+                    // D: present terms that own a dense value row (the frequent ones), S: the rest.
+                    // Documents touched by an S term ("exception" documents, few) are summed in
+                    // shared memory exactly as before, the D terms' values GATHERED for them from the
+                    // rows, all in query order.  Every other document of the block can only match D
+                    // terms: its sum is formed in registers straight from the rows (absent = -0.0f),
+                    // tested against the threshold and dropped -- no accumulator is stored, re-read
+                    // or zeroed for it.  With pruning (level >= 2) the register pass is skipped when
+                    // the D terms' block maxima, summed in query order, stay below the threshold.
                     const unsigned present = __ballot_sync(0xFFFFFFFFu, e.len > 0);
-                    const unsigned smask = present & ~ne_mask;
-                    if (ne_mask && smask == 0u) {  // only NE terms occur in this block
-                        n_skipped++;
-                        continue;
-                    }
+                    const unsigned dmask = __ballot_sync(0xFFFFFFFFu, dslot >= 0);
+                    const unsigned smask = present & ~dmask;
                     const int s_total = warp_sum(((smask >> lane) & 1u) ? e.len : 0);
-                    const int ne_total = warp_sum(((ne_mask >> lane) & 1u) ? e.len : 0);
-                    if (ne_mask && s_total <= kMsListCap && ne_total > 2 * s_total + 64) {
-                        // phase 1: bitmap of the documents any S term touches
-                        for (unsigned mm = smask; mm; mm &= mm - 1) {
-                            const int i = __ffs(mm) - 1;
-                            const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
-                            const long long s = shfl_ll(e.start, i);
-                            for (int j = lane; j < len; j += 32) {
-                                const int o = ld_nc_s32(a.indices + s + j) - doc_base;
-                                atomicOr(&cbm[o >> 5], 1u << (o & 31));
-                            }
-                        }
-                        __syncwarp();
-                        unsigned word = cbm[lane];
-                        cbm[lane] = 0u;
-                        const int cnt = __popc(word);
-                        int incl = cnt;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                            if (lane >= d) incl += y;
-                        }
-                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                        int p = incl - cnt;
-                        while (word) {
-                            const int b = __ffs(word) - 1;
-                            word &= word - 1;
-                            clist[p++] = (uint16_t)(lane * 32 + b);
-                        }
-                        __syncwarp();
-                        // phase 2: all terms in query order
-                        for (int i = 0; i < m; i++) {
-                            const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
-                            if (!len) continue;
-                            if ((ne_mask >> i) & 1u) {
-                                const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
-                                const float *dv = a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base;
-                                for (int c = lane; c < total; c += 32) {
-                                    const int o = clist[c];
-                                    acc[o] = __fadd_rn(acc[o], ld_nc_f32(dv + o));
-                                }
-                            } else {  // S terms are short here (s_total <= kMsListCap)
+                    if (s_total <= kMsListCap) {
+                        unsigned int *mcnt = a.cand_cnt + q;
+                        unsigned long long *mrow = a.cand_key + (size_t)q * (size_t)a.cap;
+                        unsigned keep_word = 0u;  // lane L: bitmap word L of the exception documents
+                        if (smask) {
+                            // phase 1: bitmap + compacted list of the documents any S term touches
+                            for (unsigned mm = smask; mm; mm &= mm - 1) {
+                                const int i = __ffs(mm) - 1;
+                                const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
                                 const long long s = shfl_ll(e.start, i);
-                                scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                                for (int j = lane; j < len; j += 32) {
+                                    const int o = ld_nc_s32(a.indices + s + j) - doc_base;
+                                    atomicOr(&cbm[o >> 5], 1u << (o & 31));
+                                }
+                            }
+                            __syncwarp();
+                            unsigned word = cbm[lane];
+                            cbm[lane] = 0u;
+                            keep_word = word;
+                            const int cnt = __popc(word);
+                            int incl = cnt;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                                if (lane >= d) incl += y;
+                            }
+                            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                            int p = incl - cnt;
+                            while (word) {
+                                const int b = __ffs(word) - 1;
+                                word &= word - 1;
+                                clist[p++] = (uint16_t)(lane * 32 + b);
+                            }
+                            __syncwarp();
+                            // phase 2: exception documents, all terms in query order
+                            for (int i = 0; i < m; i++) {
+                                const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
+                                if (!len) continue;
+                                if ((dmask >> i) & 1u) {
+                                    const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
+                                    const float *dv = a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base;
+                                    for (int c = lane; c < total; c += 32) {
+                                        const int o = clist[c];
+                                        acc[o] = __fadd_rn(acc[o], ld_nc_f32(dv + o));
+                                    }
+                                } else {
+                                    const long long s = shfl_ll(e.start, i);
+                                    scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
+                                }
+                                __syncwarp();
+                            }
+                            for (int c = lane; c < total; c += 32) {
+                                const int o = clist[c];
+                                const float v = acc[o];
+                                acc[o] = 0.f;
+                                emit_if_candidate(v, (uint32_t)(doc_base + o), thr_score, thr, mcnt, mrow, a.cap);
                             }
                             __syncwarp();
                         }
-                        // epilogue over the candidates only (they are exactly the touched documents)
-                        unsigned int *mcnt = a.cand_cnt + q;
-                        unsigned long long *mrow = a.cand_key + (size_t)q * (size_t)a.cap;
-                        for (int c = lane; c < total; c += 32) {
-                            const int o = clist[c];
-                            const float v = acc[o];
-                            acc[o] = 0.f;
-                            emit_if_candidate(v, (uint32_t)(doc_base + o), thr_score, thr, mcnt, mrow, a.cap);
+                        // phase 3: documents that match D terms only, summed in registers
+                        bool run_dense = dmask != 0u;
+                        if (run_dense && a.prune >= 2 && thr_score != 0u) {
+                            float dub = 0.f;
+                            for (unsigned mm = dmask; mm; mm &= mm - 1)
+                                dub = __fadd_rn(dub, __shfl_sync(0xFFFFFFFFu, e.bmax, __ffs(mm) - 1));
+                            if (__fmul_rn(dub, 1.00001f) < __uint_as_float(thr_score)) {
+                                run_dense = false;
+                                n_ms++;
+                            }
                         }
-                        __syncwarp();
-                        n_ms++;
+                        if (run_dense) {
+#pragma unroll 1
+                            for (int c = 0; c < kBlockDocs / 128; c++) {
+                                const int w = c * 32 + lane;
+                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                for (unsigned mm = dmask; mm; mm &= mm - 1) {  // ascending position = query order
+                                    const int slot = __shfl_sync(0xFFFFFFFFu, dslot, __ffs(mm) - 1);
+                                    const float4 r = ld_nc_f4(
+                                        reinterpret_cast<const float4 *>(a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base) + w);
+                                    v.x = __fadd_rn(v.x, r.x);
+                                    v.y = __fadd_rn(v.y, r.y);
+                                    v.z = __fadd_rn(v.z, r.z);
+                                    v.w = __fadd_rn(v.w, r.w);
+                                }
+                                // exception documents were handled above: bits (lane&7)*4.. of word c*4 + lane/8
+                                const unsigned bw = __shfl_sync(0xFFFFFFFFu, keep_word, c * 4 + (lane >> 3));
+                                const unsigned nib = (bw >> ((lane & 7) * 4)) & 15u;
+                                if (nib & 1u) v.x = 0.f;
+                                if (nib & 2u) v.y = 0.f;
+                                if (nib & 4u) v.z = 0.f;
+                                if (nib & 8u) v.w = 0.f;
+                                const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                                if (mx > 0.f && __float_as_uint(mx) >= thr_score)
+                                    emit_quad(v, (uint32_t)(doc_base + w * 4), thr_score, thr, mcnt, mrow, a.cap);
+                            }
+                        }
                         continue;
                     }
                 }
@@ -917,7 +946,7 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t 
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-    const bool ms = a.prune >= 2 && a.dense_vals != nullptr;
+    const bool ms = a.split && a.dense_vals != nullptr;
     const size_t smem = (size_t)BK_WARPS * (ms ? warp_smem_bytes<true>() : warp_smem_bytes<false>());
     int per_sm = ms ? 5 : 6;
     if (const char *e = getenv("BB25_CTAS_PER_SM")) {
@@ -1432,6 +1461,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.cand_key = d_keys;
     ba.cap = cap;
     ba.prune = idx->prune;
+    ba.split = 0;
+    if (const char *e = getenv("BB25_SPLIT")) ba.split = atoi(e) ? 1 : 0;
     ba.dense_slot = idx->dense_slot;
     ba.dense_vals = idx->dense_vals;
     ba.dense_stride = idx->dense_stride;
