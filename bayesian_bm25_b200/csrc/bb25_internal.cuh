@@ -135,13 +135,14 @@ __host__ __device__ inline uint32_t key_tf(unsigned long long k) { return (uint3
 
 // k-th largest of n distinct 64-bit keys held in shared memory (n >= k >= 1): MSB-first
 // radix select, 8 passes of 8 bits, one 256-bin histogram per pass.  All threads of the
-// block must call it; hist = 256 words, st = 2 words of shared scratch.
+// block must call it; hist = 256 words, st = 2 words of shared scratch.  With passes < 8
+// only the top 8*passes bits of the k-th largest key are resolved (the rest are 0).
 template <int NT>
 __device__ unsigned long long block_kth_largest(const unsigned long long *keys, int n, int k, unsigned int *hist,
-                                                unsigned int *st, int tid) {
+                                                unsigned int *st, int tid, int passes = 8) {
     unsigned long long prefix = 0ull, mask = 0ull;
     unsigned int rem = (unsigned int)k;
-    for (int pass = 0; pass < 8; pass++) {
+    for (int pass = 0; pass < passes; pass++) {
         const int shift = 56 - 8 * pass;
         for (int i = tid; i < 256; i += NT) hist[i] = 0u;
         __syncthreads();

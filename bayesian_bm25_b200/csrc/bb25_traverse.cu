@@ -75,6 +75,18 @@ __device__ __forceinline__ float4 ld_nc_f4(const float4 *p) {
     return r;
 }
 
+// Dense value rows are shared by every warp of the SM working on the same block (items are
+// block-major), so unlike the posting streams they are worth keeping in L1.
+__device__ __forceinline__ float4 ld_row_f4(const float4 *p) {
+#if defined(BB25_ROW_NOALLOC)
+    return ld_nc_f4(p);
+#else
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#endif
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void rmw1(float *acc, uint8_t *cnt, int off, float v) {
     acc[off] = __fadd_rn(acc[off], v);
@@ -288,7 +300,9 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
                                     const float *__restrict__ kth, int32_t *__restrict__ qt_ws,
                                     uint8_t *__restrict__ nocount, unsigned long long *__restrict__ thr,
                                     unsigned int *__restrict__ cand_cnt, unsigned int *__restrict__ n_prev,
-                                    int *err) {
+                                    int *err, const int64_t *__restrict__ indptr = nullptr,
+                                    const int32_t *__restrict__ dense_slot = nullptr,
+                                    longlong2 *__restrict__ qt_info = nullptr) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_q) return;
     const int64_t t0 = q_off[q], t1 = q_off[q + 1];
@@ -304,6 +318,9 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
         for (int64_t j = t0; j < i && !dup; j++) dup = (q_terms[j] == t);
         qt_ws[i - term_base] = t;
         nocount[i - term_base] = dup ? 1 : 0;
+        // per query term: posting-list start and dense-row slot, so that the traversal reads them
+        // alongside the term id instead of after it
+        if (qt_info) qt_info[i - term_base] = make_longlong2(indptr[t], dense_slot ? (long long)dense_slot[t] : -1ll);
         if (kth) {
             uint32_t b = __float_as_uint(kth[t]);
             best = b > best ? b : best;
@@ -340,6 +357,10 @@ struct SelectArgs {
     // tf_search != 0: keys carry no matched-term count; recover it for the winners by
     // searching each distinct query term's posting list inside the document's tile
     int tf_search;
+    // rescore != 0: keys [n_prev, n) carry order-free sums (block_kernel's relaxed mode); replace
+    // them by the exact query-order score and drop the ones that miss the threshold
+    int rescore;
+    const float *data;
     const int32_t *indices;
     const int64_t *indptr;
     const uint2 *blk_tab;
@@ -385,6 +406,44 @@ __device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t d
     return c;
 }
 
+// bm25s's score of one (query, document): the values of the query's terms at the document,
+// added in query order in fp32 (the order block_kernel's relaxed mode does not keep).  Warp
+// cooperative: lane i looks term i up -- dense value row, or binary search inside the
+// document's block slice -- and the sum runs over the lanes in order.  Absent terms add
+// +-0.0f, which leaves a non-negative sum unchanged.
+__device__ inline float exact_score_warp(const SelectArgs &a, int q, uint32_t doc, int lane) {
+    const long long t0 = a.q_off[q] - a.term_base, t1 = a.q_off[q + 1] - a.term_base;
+    const uint2 *row = a.blk_tab + (size_t)(doc / (uint32_t)kBlockDocs) * (size_t)a.n_vocab;
+    float s = 0.f;
+    for (long long b0 = t0; b0 < t1; b0 += 32) {
+        const int nb = (int)min(32ll, t1 - b0);
+        float val = 0.f;
+        if (lane < nb) {
+            const int t = a.q_terms[b0 + lane];
+            const int slot = a.dense_slot ? a.dense_slot[t] : -1;
+            if (slot >= 0) {
+                val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + doc];
+            } else {
+                const uint2 ent = row[t];
+                const int len = (int)(ent.y & kBlkLenMask);
+                if (len) {
+                    long long lo = a.indptr[t] + (long long)ent.x;
+                    const long long end = lo + len;
+                    long long hi = end;
+                    while (lo < hi) {
+                        const long long mid = (lo + hi) >> 1;
+                        if ((uint32_t)a.indices[mid] < doc) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    if (lo < end && (uint32_t)a.indices[lo] == doc) val = a.data[lo];
+                }
+            }
+        }
+        for (int i = 0; i < nb; i++) s = __fadd_rn(s, __shfl_sync(0xFFFFFFFFu, val, i));
+    }
+    return s;
+}
+
 template <int NT>
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int P, int tid) {
     for (int size = 2; size <= P; size <<= 1) {
@@ -405,7 +464,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int 
 }
 
 // Shared-memory plan of select_kernel: keys u64[cap] | top u64[kpad] | hist u32[256] |
-// st u32[4] | flag u8[kpad]   (kpad = k rounded up to a power of two)
+// st u32[4] | flag u8[kpad] | list u16[cap]   (kpad = k rounded up to a power of two)
 template <int NT>
 __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ SelectArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -424,21 +483,134 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     unsigned long long *row = a.cand_key + (size_t)q * (size_t)a.cap;
     const bool overflow = n_raw > (unsigned)a.cap;
 
-    if (!overflow && !a.final_pass && n <= k) {
+    if (!a.rescore && !overflow && !a.final_pass && n <= k) {
         // nothing to drop and no tighter bound to learn yet
         if (tid == 0) a.n_prev[q] = (unsigned int)n;
         return;
     }
     for (int i = tid; i < n; i += NT) keys[i] = row[i];
+    if (tid == 0) st[3] = 0u;
     __syncthreads();
+    int n_valid = n;
+    if (a.rescore) {
+        // the keys added since the last selection carry order-free sums: one warp per key
+        // recomputes the exact score; keys that miss the threshold become 0 (= empty)
+        const unsigned long long thr64 = a.thr[q];
+        const int lane = tid & 31;
+        const long long t0 = a.q_off[q] - a.term_base;
+        const int m = (int)(a.q_off[q + 1] - a.term_base - t0);
+        const int n0 = (int)a.n_prev[q];
+        // Keys that cannot be among the best k need no exact score: with T the k-th largest
+        // key as it stands (order-free sums are within 4e-6 relative of the exact ones for
+        // m <= 32), a new key below T * (1 - 3e-5) is strictly below k documents' exact
+        // scores.  Longer queries were summed in query order already (margin unused).
+        uint32_t cut_bits = 0u;
+        if (n >= k && m <= 32) {
+            const unsigned long long ta = block_kth_largest<NT>(keys, n, k, hist, st, tid, 4);  // score bits suffice
+            cut_bits = __float_as_uint(__fmul_rn(__uint_as_float(key_score_bits(ta)), 0.99997f));
+            __syncthreads();
+        }
+        uint16_t *list = reinterpret_cast<uint16_t *>(flag + kpad);
+        if (tid == 0) st[2] = 0u;
+        __syncthreads();
+        for (int i = n0 + tid; i < n; i += NT) {
+            if (key_score_bits(keys[i]) >= cut_bits) list[atomicAdd(&st[2], 1u)] = (uint16_t)i;
+            else keys[i] = 0ull;
+        }
+        __syncthreads();
+        const int n_list = (int)st[2];
+        if (m <= 32) {
+            // a group of g = 2^ceil(log2 m) lanes per key, lane j of the group looks term j up
+            int g = 1;
+            while (g < m) g <<= 1;
+            const int sub = lane / g, j = lane % g;
+            const int groups = (NT / 32) * (32 / g);
+            const int gid = (tid >> 5) * (32 / g) + sub;
+            int t = 0, slot = -1;
+            long long ip = 0;
+            if (j < m) {
+                t = a.q_terms[t0 + j];
+                slot = a.dense_slot ? a.dense_slot[t] : -1;
+                if (slot < 0) ip = a.indptr[t];
+            }
+            for (int base = 0; base < n_list; base += groups) {
+                const bool act = base + gid < n_list;
+                const int i = act ? (int)list[base + gid] : 0;
+                float val = 0.f;
+                uint32_t id = 0;
+                if (act) {
+                    id = key_local_id(keys[i]);
+                    if (j < m) {
+                        if (slot >= 0) {
+                            val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + id];
+                        } else {
+                            const uint2 ent = a.blk_tab[(size_t)(id / (uint32_t)kBlockDocs) * (size_t)a.n_vocab + t];
+                            const int len = (int)(ent.y & kBlkLenMask);
+                            if (len) {
+                                long long lo = ip + (long long)ent.x;
+                                const long long end = lo + len;
+                                long long hi = end;
+                                while (lo < hi) {
+                                    const long long mid = (lo + hi) >> 1;
+                                    if ((uint32_t)a.indices[mid] < id) lo = mid + 1;
+                                    else hi = mid;
+                                }
+                                if (lo < end && (uint32_t)a.indices[lo] == id) val = a.data[lo];
+                            }
+                        }
+                    }
+                }
+                float sc = 0.f;
+                for (int u = 0; u < m; u++) sc = __fadd_rn(sc, __shfl_sync(0xFFFFFFFFu, val, sub * g + u));
+                if (act && j == 0) {
+                    const uint32_t bits = __float_as_uint(sc);
+                    unsigned long long key = make_key(bits, id, 0u);
+                    if (bits == 0u || key < thr64) key = 0ull;
+                    keys[i] = key;
+                }
+            }
+        } else {
+            for (int c = tid >> 5; c < n_list; c += NT / 32) {
+                const int i = (int)list[c];
+                const uint32_t id = key_local_id(keys[i]);
+                const uint32_t bits = __float_as_uint(exact_score_warp(a, q, id, lane));
+                unsigned long long key = make_key(bits, id, 0u);
+                if (bits == 0u || key < thr64) key = 0ull;
+                if (lane == 0) keys[i] = key;
+            }
+        }
+        __syncthreads();
+        unsigned int c = 0;
+        for (int i = tid; i < n; i += NT) c += keys[i] != 0ull;
+        if (c) atomicAdd(&st[3], c);
+        __syncthreads();
+        n_valid = (int)st[3];
+        if (!overflow && !a.final_pass && n_valid <= k) {
+            // keep the exact keys, compacted; no tighter bound to learn yet
+            if (tid == 0) st[2] = 0u;
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) {
+                const unsigned long long key = keys[i];
+                if (key) row[atomicAdd(&st[2], 1u)] = key;
+            }
+            if (tid == 0) {
+                a.cand_cnt[q] = (unsigned int)n_valid;
+                a.n_prev[q] = (unsigned int)n_valid;
+            }
+            return;
+        }
+    }
     unsigned long long kth = 0ull;
-    if (n >= k) kth = block_kth_largest<NT>(keys, n, k, hist, st, tid);
+    if (n_valid >= k) kth = block_kth_largest<NT>(keys, n, k, hist, st, tid);
 
     if (overflow) {
         // more candidates than the row holds: the k-th best of the stored ones is a
-        // valid, strictly tighter bound; redo this tile group for this query
+        // valid bound, strictly tighter when the keys are exact; the host redoes this group
+        // for this query in query order (exact keys against the full 64-bit threshold), which
+        // always converges
         if (tid == 0) {
-            a.thr[q] = kth & ~15ull;
+            const unsigned long long t = kth & ~15ull;
+            if (t > a.thr[q]) a.thr[q] = t;
             a.cand_cnt[q] = a.n_prev[q];
             const unsigned int pos = atomicAdd(a.n_over, 1u);
             a.over_list[pos] = q;
@@ -451,7 +623,7 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         __syncthreads();
         for (int i = tid; i < n; i += NT) {
             const unsigned long long key = keys[i];
-            if (key >= kth) row[atomicAdd(&st[2], 1u)] = key;
+            if (key != 0ull && key >= kth) row[atomicAdd(&st[2], 1u)] = key;
         }
         if (tid == 0) {
             a.cand_cnt[q] = (unsigned int)k;
@@ -462,13 +634,13 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         return;
     }
     // final pass: the best min(n, k) keys, sorted
-    const int n_pos = min(n, k);
+    const int n_pos = min(n_valid, k);
     if (tid == 0) st[2] = 0u;
     for (int i = tid; i < kpad; i += NT) top[i] = 0ull;
     __syncthreads();
     for (int i = tid; i < n; i += NT) {
         const unsigned long long key = keys[i];
-        if (key >= kth) top[atomicAdd(&st[2], 1u)] = key;
+        if (key != 0ull && key >= kth) top[atomicAdd(&st[2], 1u)] = key;
     }
     __syncthreads();
     int P = 2;
@@ -524,18 +696,27 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
 //      bound is below the query's threshold (block-max pruning; exact because fp32
 //      addition of non-negative values is monotone), or when no term has a posting
 //      in the block,
-//   3. otherwise adds the terms' posting slices in query order (a __syncwarp between
-//      terms is all the ordering needs: one warp owns every document of the block),
-//   4. scans its 1024 accumulators, emits keys >= threshold and zeroes them.
-// No block-level barrier anywhere; 48 resident warps per SM hide each other's L2
-// latency.  Items are block-major, so the whole chip works on a handful of adjacent
-// blocks whose index slices sit in L2.
+//   3. otherwise evaluates the unit, in one of two instantiations:
+//      EXACT = false (first evaluation of every block group).  Sums are formed in ANY
+//        order: terms without a dense value row are scattered into the accumulators, then
+//        one pass adds the dense rows of the frequent terms to them IN REGISTERS (FADD2),
+//        tests the result against 0.99999 x threshold and drops it -- the frequent terms
+//        never touch shared memory.  Any order of <= 32 non-negative fp32 additions is
+//        within 4e-6 relative of the query-order sum, so no qualifying document is missed;
+//        select_kernel then replaces each emitted key's sum by the exact query-order score
+//        (bm25s's arithmetic) before anything is ranked or a threshold is raised.
+//      EXACT = true (threshold repair after a candidate-row overflow, and indexes without
+//        dense rows).  Posting slices / dense rows are added in query order (a __syncwarp
+//        between terms is all the ordering needs: one warp owns every document of the
+//        block), the 1024 accumulators are scanned, keys >= the 64-bit threshold emitted.
+// No block-level barrier anywhere.  Items are block-major, so the whole chip works on a
+// handful of adjacent blocks whose index slices and value rows sit in L2 / L1.
 // =================================================================================
 #ifndef BB25_QC
 #define BB25_QC 8
 #endif
 constexpr int QC = BB25_QC;  // queries per warp work item
-constexpr int BK_WARPS = 8;  // warps per CTA (6 CTAs/SM -> 48 warps, 192 KB of accumulators)
+constexpr int BK_WARPS = 8;  // warps per CTA (4 KB of accumulators per warp)
 
 struct BlockArgs {
     const float *data;
@@ -544,6 +725,7 @@ struct BlockArgs {
     const uint2 *blk_tab;
     int64_t n_vocab;
     const int32_t *q_terms;  // sanitised copy, indexed by absolute position - term_base
+    const longlong2 *qt_info;  // per query term: (indptr[t], dense slot or -1)
     const int64_t *q_off;
     int64_t term_base;
     const int32_t *q_list;
@@ -553,8 +735,7 @@ struct BlockArgs {
     unsigned int *cand_cnt;
     unsigned long long *cand_key;
     int cap;
-    int split;  // 1: split evaluation (register sums for documents matching frequent terms only)
-    int prune;  // 0 exhaustive, 1 block-max skip, 2 + dense-pass skip by the frequent terms' bound
+    int prune;  // 0 exhaustive, 1 block-max skip, 2 + skip of frequent-term-only documents by their bound
     const int32_t *dense_slot;
     const float *dense_vals;
     int64_t dense_stride;
@@ -562,12 +743,7 @@ struct BlockArgs {
     unsigned long long *stats;  // [0] units visited, [1] pruned by the block-max bound, [2] MaxScore units
 };
 
-// per-warp shared memory: 1024 fp32 accumulators [+ candidate list u16[512] + bitmap u32[32]]
-constexpr int kMsListCap = 512;
-template <bool MS>
-__host__ __device__ constexpr int warp_smem_bytes() {
-    return kBlockDocs * 4 + (MS ? kMsListCap * 2 + 128 : 0);
-}
+// per-warp shared memory: 1024 fp32 accumulators
 
 __device__ __forceinline__ long long shfl_ll(long long v, int src) {
     int lo = __shfl_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), src);
@@ -638,11 +814,35 @@ __device__ __forceinline__ void dense_add_warp(const float *__restrict__ row, fl
     }
 }
 
+// postings [s, s+len) of one term into the warp's block accumulators, up to 64 postings per
+// round of loads (no alignment peel: a short slice must not cost two dependent rounds)
+template <bool FRESH>
+__device__ __forceinline__ void scatter_block(const float *__restrict__ data, const int32_t *__restrict__ indices,
+                                              long long s, int len, float *acc, int doc_base, int lane) {
+    const int32_t *ip = indices + s;
+    const float *dp = data + s;
+    for (int j0 = 0; j0 < len; j0 += 64) {
+        int d[2];
+        float v[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int j = j0 + 32 * u + lane;
+            if (j < len) {
+                d[u] = ld_nc_s32(ip + j);
+                v[u] = ld_nc_f32(dp + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+            if (j0 + 32 * u + lane < len) acc_add<FRESH>(acc, d[u] - doc_base, v[u]);
+    }
+}
+
 struct TermEnt {
     long long start;
     int len;
     float bmax;
-    int term;
+    int dslot;  // dense value row of the term (-1: none, or no posting in this block)
 };
 
 __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uint2 *row, long long pos, bool active) {
@@ -650,14 +850,15 @@ __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uin
     e.start = 0;
     e.len = 0;
     e.bmax = 0.f;
-    e.term = 0;
+    e.dslot = -1;
     if (active) {
         const int t = a.q_terms[pos];
+        const longlong2 info = a.qt_info[pos];
         const uint2 ent = row[t];
-        e.term = t;
         e.len = (int)(ent.y & kBlkLenMask);
         e.bmax = __uint_as_float(ent.y & ~kBlkLenMask);
-        e.start = a.indptr[t] + (long long)ent.x;
+        e.start = info.x + (long long)ent.x;
+        e.dslot = e.len > 0 ? (int)info.y : -1;
     }
     return e;
 }
@@ -682,32 +883,122 @@ __device__ __forceinline__ void emit_if_candidate(float v, uint32_t local_id, ui
     }
 }
 
-// rare path of the register epilogue, kept out of line so it does not cost registers
-__device__ __noinline__ void emit_quad(float4 v, uint32_t first_id, uint32_t thr_score, unsigned long long thr,
-                                       unsigned int *ccnt, unsigned long long *crow, int cap) {
-    emit_if_candidate(v.x, first_id + 0, thr_score, thr, ccnt, crow, cap);
-    emit_if_candidate(v.y, first_id + 1, thr_score, thr, ccnt, crow, cap);
-    emit_if_candidate(v.z, first_id + 2, thr_score, thr, ccnt, crow, cap);
-    emit_if_candidate(v.w, first_id + 3, thr_score, thr, ccnt, crow, cap);
+#ifndef BB25_PASS_CHUNKS
+#define BB25_PASS_CHUNKS 2
+#endif
+constexpr int kPassChunks = BB25_PASS_CHUNKS;  // 128-document chunks in flight per round of the order-free pass
+
+// rare path of the order-free pass, kept out of line so it does not cost registers: keys carry
+// the any-order sum; select_kernel replaces it by the exact score before anything is ranked
+__device__ __noinline__ void emit_quad_relaxed(float4 v, uint32_t first_id, uint32_t thr_rel, unsigned int *cand_cnt,
+                                               unsigned long long *cand_key, int q, int cap) {
+    unsigned int *ccnt = cand_cnt + q;
+    unsigned long long *crow = cand_key + (size_t)q * (size_t)cap;
+    const float av[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t bits = __float_as_uint(av[c]);
+        if (bits != 0u && bits >= thr_rel) {
+            const unsigned int pos = atomicAdd(ccnt, 1u);
+            if (pos < (unsigned)cap) crow[pos] = make_key(bits, first_id + c, 0u);
+        }
+    }
 }
 
-template <int WARPS, bool MS>
-__global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __grid_constant__ BlockArgs a) {
+// fp32 x 2 add (Blackwell FADD2): the same round-to-nearest result per element as two FADDs
+__device__ __forceinline__ void add_f4(float4 &v, const float4 &r) {
+    unsigned long long a0, a1, b0, b1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(v.x), "f"(v.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(v.z), "f"(v.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b0) : "f"(r.x), "f"(r.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b1) : "f"(r.z), "f"(r.w));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(b0));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(b1));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(a1));
+}
+
+struct PassArgs {
+    float4 *acc4;          // the warp's accumulators, already offset by the lane
+    const float4 *row_a;   // first / second D term's value row at (block, lane)
+    const float4 *row_b;
+    unsigned rest;         // third and later D terms (query positions)
+    int dslot;             // lane i: dense slot of term i
+    uint32_t thr_rel;      // relaxed threshold, >= 1
+    uint32_t first_id;     // local id of the lane's first document in chunk 0
+    int q;
+};
+
+// The order-free pass over the block: per 128-document chunk, lane L owns documents 4L..4L+3.
+//   ND     D terms whose rows are added from registers (2 = two or more, the others via `rest`)
+//   HAS_S  the accumulators hold S-term sums: read them and leave zeros behind
+//   PRED   only quads with an S contribution are completed (D-only documents cannot qualify)
+template <int ND, bool HAS_S, bool PRED>
+__device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassArgs &pa, const float *dbase) {
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int h = 0; h < kBlockDocs / (128 * kPassChunks); h++) {
+        const int w0 = h * (32 * kPassChunks);
+        float4 v[kPassChunks], ra[kPassChunks], rb[kPassChunks];
+#pragma unroll
+        for (int j = 0; j < kPassChunks; j++) {
+            const int w = w0 + j * 32;
+            v[j] = HAS_S ? pa.acc4[w] : zero4;
+            if (PRED) {
+                const bool nz = fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)) > 0.f;
+                ra[j] = zero4;
+                rb[j] = zero4;
+                if (nz) {
+                    if (ND >= 1) ra[j] = ld_row_f4(pa.row_a + w);
+                    if (ND >= 2) rb[j] = ld_row_f4(pa.row_b + w);
+                }
+            } else {
+                if (ND >= 1) ra[j] = ld_row_f4(pa.row_a + w);
+                if (ND >= 2) rb[j] = ld_row_f4(pa.row_b + w);
+            }
+            if (HAS_S) pa.acc4[w] = zero4;
+        }
+#pragma unroll
+        for (int j = 0; j < kPassChunks; j++) {
+            if (ND >= 1) add_f4(v[j], ra[j]);
+            if (ND >= 2) add_f4(v[j], rb[j]);
+        }
+        if (ND >= 2) {
+            for (unsigned mm = pa.rest; mm; mm &= mm - 1) {  // third and later D terms
+                const int slot = __shfl_sync(0xFFFFFFFFu, pa.dslot, __ffs(mm) - 1);
+                const float4 *rp = reinterpret_cast<const float4 *>(dbase + (size_t)slot * (size_t)a.dense_stride);
+#pragma unroll
+                for (int j = 0; j < kPassChunks; j++) {
+                    if (!PRED || fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)) > 0.f)
+                        add_f4(v[j], ld_row_f4(rp + w0 + j * 32));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kPassChunks; j++) {
+            const float mx = fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w));
+            if (__float_as_uint(mx) >= pa.thr_rel)
+                emit_quad_relaxed(v[j], pa.first_id + (uint32_t)((w0 + j * 32) * 4), pa.thr_rel, a.cand_cnt, a.cand_key, pa.q, a.cap);
+        }
+    }
+}
+
+#ifndef BB25_BLOCK_CTAS
+#define BB25_BLOCK_CTAS 4  // resident CTAs per SM of the order-free kernel (register cap 64); measured best
+#endif
+template <int WARPS, bool EXACT>
+__global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char *wbase = smem + (size_t)warp * warp_smem_bytes<MS>();
-    float *acc = reinterpret_cast<float *>(wbase);
+    float *acc = reinterpret_cast<float *>(smem + (size_t)warp * (kBlockDocs * 4));
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
-    uint16_t *clist = reinterpret_cast<uint16_t *>(wbase + kBlockDocs * 4);
-    unsigned int *cbm = reinterpret_cast<unsigned int *>(wbase + kBlockDocs * 4 + kMsListCap * 2);
     for (int i = lane; i < kBlockDocs / 4; i += 32) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (MS) cbm[lane] = 0u;
     __syncwarp();
 
     const int n_chunks = (a.n_q + QC - 1) / QC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
-    unsigned long long n_units = 0, n_skipped = 0, n_ms = 0;
+    unsigned int n_skipped = 0, n_ms = 0;  // per warp and launch: far below 2^32
 
     for (;;) {
         long long item = 0;
@@ -718,154 +1009,113 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
         const int slot0 = (int)(item % n_chunks) * QC;
         const int nslots = min(QC, a.n_q - slot0);
         const int doc_base = blk * kBlockDocs;
-        const uint2 *row = a.blk_tab + (size_t)blk * (size_t)a.n_vocab;
 
-        // lane s holds the description of the chunk's s-th query
-        int my_q = 0, my_m = 0;
-        long long my_t0 = 0;
-        unsigned long long my_thr = 0;
+        // lane s holds the description of the chunk's s-th query (the full 64-bit threshold is
+        // re-read by the query-order path, which alone needs it)
+        int my_q = 0, my_m = 0, my_t0 = 0;
+        uint32_t my_thr_score = 0;
         if (lane < nslots) {
             my_q = a.q_list ? a.q_list[slot0 + lane] : slot0 + lane;
             const long long t0 = a.q_off[my_q];
             my_m = (int)max(0ll, (long long)a.q_off[my_q + 1] - t0);
-            my_t0 = t0 - a.term_base;
-            my_thr = a.thr[my_q];
+            my_t0 = (int)(t0 - a.term_base);
+            my_thr_score = (uint32_t)(a.thr[my_q] >> 33);
         }
 
         for (int sidx = 0; sidx < nslots; sidx++) {
             const int m = __shfl_sync(0xFFFFFFFFu, my_m, sidx);
             if (m == 0) continue;
             const int q = __shfl_sync(0xFFFFFFFFu, my_q, sidx);
-            const long long t0 = shfl_ll(my_t0, sidx);
-            const unsigned long long thr = (unsigned long long)shfl_ll((long long)my_thr, sidx);
-            const uint32_t thr_score = (uint32_t)(thr >> 33);
-            n_units++;
+            const int t0 = __shfl_sync(0xFFFFFFFFu, my_t0, sidx);
+            const uint32_t thr_score = __shfl_sync(0xFFFFFFFFu, my_thr_score, sidx);
+            const uint2 *row = a.blk_tab + (size_t)blk * (size_t)a.n_vocab;
 
             if (m <= 32) {
                 const TermEnt e = load_term_entry(a, row, t0 + lane, lane < m);
                 if (__ballot_sync(0xFFFFFFFFu, e.len > 0) == 0u) continue;  // no posting of any term in this block
-                float ub = 0.f;
-                for (int i = 0; i < m; i++) ub = __fadd_rn(ub, __shfl_sync(0xFFFFFFFFu, e.bmax, i));
-                if (a.prune && __float_as_uint(ub) < thr_score) {
-                    n_skipped++;
-                    continue;
-                }
-                const int dslot = (a.dense_vals && lane < m && e.len > 0) ? a.dense_slot[e.term] : -1;
-                if (MS && a.split) {
-                    // ---- split evaluation of the unit ------------------------------------------
-                    // D: present terms that own a dense value row (the frequent ones), S: the rest.
-                    // Documents touched by an S term ("exception" documents, few) are summed in
-                    // shared memory exactly as before, the D terms' values GATHERED for them from the
-                    // rows, all in query order.  Every other document of the block can only match D
-                    // terms: its sum is formed in registers straight from the rows (absent = -0.0f),
-                    // tested against the threshold and dropped -- no accumulator is stored, re-read
-                    // or zeroed for it.  With pruning (level >= 2) the register pass is skipped when
-                    // the D terms' block maxima, summed in query order, stay below the threshold.
-                    const unsigned present = __ballot_sync(0xFFFFFFFFu, e.len > 0);
-                    const unsigned dmask = __ballot_sync(0xFFFFFFFFu, dslot >= 0);
-                    const unsigned smask = present & ~dmask;
-                    const int s_total = warp_sum(((smask >> lane) & 1u) ? e.len : 0);
-                    if (s_total <= kMsListCap) {
-                        unsigned int *mcnt = a.cand_cnt + q;
-                        unsigned long long *mrow = a.cand_key + (size_t)q * (size_t)a.cap;
-                        unsigned keep_word = 0u;  // lane L: bitmap word L of the exception documents
-                        if (smask) {
-                            // phase 1: bitmap + compacted list of the documents any S term touches
-                            for (unsigned mm = smask; mm; mm &= mm - 1) {
-                                const int i = __ffs(mm) - 1;
-                                const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
-                                const long long s = shfl_ll(e.start, i);
-                                for (int j = lane; j < len; j += 32) {
-                                    const int o = ld_nc_s32(a.indices + s + j) - doc_base;
-                                    atomicOr(&cbm[o >> 5], 1u << (o & 31));
-                                }
-                            }
-                            __syncwarp();
-                            unsigned word = cbm[lane];
-                            cbm[lane] = 0u;
-                            keep_word = word;
-                            const int cnt = __popc(word);
-                            int incl = cnt;
-#pragma unroll
-                            for (int d = 1; d < 32; d <<= 1) {
-                                const int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                                if (lane >= d) incl += y;
-                            }
-                            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                            int p = incl - cnt;
-                            while (word) {
-                                const int b = __ffs(word) - 1;
-                                word &= word - 1;
-                                clist[p++] = (uint16_t)(lane * 32 + b);
-                            }
-                            __syncwarp();
-                            // phase 2: exception documents, all terms in query order
-                            for (int i = 0; i < m; i++) {
-                                const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
-                                if (!len) continue;
-                                if ((dmask >> i) & 1u) {
-                                    const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
-                                    const float *dv = a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base;
-                                    for (int c = lane; c < total; c += 32) {
-                                        const int o = clist[c];
-                                        acc[o] = __fadd_rn(acc[o], ld_nc_f32(dv + o));
-                                    }
-                                } else {
-                                    const long long s = shfl_ll(e.start, i);
-                                    scatter_warp(a.data, a.indices, s, len, acc, doc_base, lane);
-                                }
-                                __syncwarp();
-                            }
-                            for (int c = lane; c < total; c += 32) {
-                                const int o = clist[c];
-                                const float v = acc[o];
-                                acc[o] = 0.f;
-                                emit_if_candidate(v, (uint32_t)(doc_base + o), thr_score, thr, mcnt, mrow, a.cap);
-                            }
-                            __syncwarp();
-                        }
-                        // phase 3: documents that match D terms only, summed in registers
-                        bool run_dense = dmask != 0u;
-                        if (run_dense && a.prune >= 2 && thr_score != 0u) {
-                            float dub = 0.f;
-                            for (unsigned mm = dmask; mm; mm &= mm - 1)
-                                dub = __fadd_rn(dub, __shfl_sync(0xFFFFFFFFu, e.bmax, __ffs(mm) - 1));
-                            if (__fmul_rn(dub, 1.00001f) < __uint_as_float(thr_score)) {
-                                run_dense = false;
-                                n_ms++;
-                            }
-                        }
-                        if (run_dense) {
-#pragma unroll 1
-                            for (int c = 0; c < kBlockDocs / 128; c++) {
-                                const int w = c * 32 + lane;
-                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                                for (unsigned mm = dmask; mm; mm &= mm - 1) {  // ascending position = query order
-                                    const int slot = __shfl_sync(0xFFFFFFFFu, dslot, __ffs(mm) - 1);
-                                    const float4 r = ld_nc_f4(
-                                        reinterpret_cast<const float4 *>(a.dense_vals + (size_t)slot * (size_t)a.dense_stride + doc_base) + w);
-                                    v.x = __fadd_rn(v.x, r.x);
-                                    v.y = __fadd_rn(v.y, r.y);
-                                    v.z = __fadd_rn(v.z, r.z);
-                                    v.w = __fadd_rn(v.w, r.w);
-                                }
-                                // exception documents were handled above: bits (lane&7)*4.. of word c*4 + lane/8
-                                const unsigned bw = __shfl_sync(0xFFFFFFFFu, keep_word, c * 4 + (lane >> 3));
-                                const unsigned nib = (bw >> ((lane & 7) * 4)) & 15u;
-                                if (nib & 1u) v.x = 0.f;
-                                if (nib & 2u) v.y = 0.f;
-                                if (nib & 4u) v.z = 0.f;
-                                if (nib & 8u) v.w = 0.f;
-                                const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-                                if (mx > 0.f && __float_as_uint(mx) >= thr_score)
-                                    emit_quad(v, (uint32_t)(doc_base + w * 4), thr_score, thr, mcnt, mrow, a.cap);
-                            }
-                        }
+                if (a.prune) {
+                    float ub = 0.f;
+                    for (int i = 0; i < m; i++) ub = __fadd_rn(ub, __shfl_sync(0xFFFFFFFFu, e.bmax, i));
+                    if (__float_as_uint(ub) < thr_score) {
+                        n_skipped++;
                         continue;
                     }
                 }
+                const int dslot = e.dslot;
+                if (!EXACT) {
+                    // ---- order-free evaluation of the unit ---------------------------------------
+                    // The candidates this kernel emits are re-scored exactly (query order) by
+                    // select_kernel, so here a document's sum may be formed in ANY order as long as
+                    // no document whose exact score reaches the threshold is missed: m <= 32 fp32
+                    // additions of non-negative values differ between orders by < 2*31*2^-24
+                    // relative, hence "sum >= 0.99999 * threshold" keeps them all.  That freedom
+                    // lets the frequent terms (D, with a dense value row) stay out of shared
+                    // memory: the other terms (S) are scattered into the warp's accumulators, and
+                    // one pass adds the D rows to them in registers, tests and drops the result.
+                    const unsigned present = __ballot_sync(0xFFFFFFFFu, e.len > 0);
+                    const unsigned dmask = __ballot_sync(0xFFFFFFFFu, dslot >= 0);
+                    const unsigned smask = present & ~dmask;
+                    bool first = true;
+                    for (unsigned mm = smask; mm; mm &= mm - 1) {
+                        const int i = __ffs(mm) - 1;
+                        const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
+                        const long long s = shfl_ll(e.start, i);
+                        if (first) scatter_block<true>(a.data, a.indices, s, len, acc, doc_base, lane);
+                        else scatter_block<false>(a.data, a.indices, s, len, acc, doc_base, lane);
+                        first = false;
+                        __syncwarp();
+                    }
+                    // documents matching D terms only cannot qualify when the D terms' block maxima,
+                    // summed in query order, stay below the threshold (pruning level >= 2): then
+                    // only quads holding an S contribution are completed
+                    bool dense_all = dmask != 0u;
+                    if (dense_all && a.prune >= 2 && thr_score != 0u) {
+                        float dub = 0.f;
+                        for (unsigned mm = dmask; mm; mm &= mm - 1)
+                            dub = __fadd_rn(dub, __shfl_sync(0xFFFFFFFFu, e.bmax, __ffs(mm) - 1));
+                        if (__float_as_uint(dub) < thr_score) {
+                            dense_all = false;
+                            n_ms++;
+                        }
+                    }
+                    if (!smask && !dense_all) continue;
+                    const uint32_t thr_rel =
+                        thr_score ? __float_as_uint(__fmul_rn(__uint_as_float(thr_score), 0.99999f)) : 1u;
+                    const int n_d = __popc(dmask);
+                    PassArgs pa;
+                    pa.acc4 = acc4 + lane;
+                    pa.thr_rel = thr_rel;
+                    pa.first_id = (uint32_t)(doc_base + lane * 4);
+                    pa.q = q;
+                    pa.rest = 0u;
+                    pa.dslot = dslot;
+                    const float *dbase = a.dense_vals + doc_base + lane * 4;
+                    if (n_d >= 1)
+                        pa.row_a = reinterpret_cast<const float4 *>(
+                            dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(dmask) - 1) * (size_t)a.dense_stride);
+                    if (n_d >= 2) {
+                        const unsigned d2 = dmask & (dmask - 1);
+                        pa.row_b = reinterpret_cast<const float4 *>(
+                            dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(d2) - 1) * (size_t)a.dense_stride);
+                        pa.rest = d2 & (d2 - 1);
+                    }
+                    if (!smask) {
+                        if (n_d == 1) order_free_pass<1, false, false>(a, pa, dbase);
+                        else order_free_pass<2, false, false>(a, pa, dbase);
+                    } else if (n_d == 0) {
+                        order_free_pass<0, true, false>(a, pa, dbase);
+                    } else if (dense_all) {
+                        if (n_d == 1) order_free_pass<1, true, false>(a, pa, dbase);
+                        else order_free_pass<2, true, false>(a, pa, dbase);
+                    } else {
+                        if (n_d == 1) order_free_pass<1, true, true>(a, pa, dbase);
+                        else order_free_pass<2, true, true>(a, pa, dbase);
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 bool fresh = true;  // accumulators all zero until the first term with postings here
-                for (int i = 0; i < m; i++) {
+                for (int i = 0; EXACT && i < m; i++) {
                     const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
                     const long long s = shfl_ll(e.start, i);
                     const int slot = __shfl_sync(0xFFFFFFFFu, dslot, i);
@@ -906,9 +1156,24 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
                         __syncwarp();
                     }
                 }
+                if (!EXACT) {
+                    // every term went through the accumulators (any order is fine here too)
+                    PassArgs pa;
+                    pa.acc4 = acc4 + lane;
+                    pa.thr_rel = thr_score ? __float_as_uint(__fmul_rn(__uint_as_float(thr_score), 0.99999f)) : 1u;
+                    pa.first_id = (uint32_t)(doc_base + lane * 4);
+                    pa.q = q;
+                    pa.rest = 0u;
+                    pa.dslot = -1;
+                    order_free_pass<0, true, false>(a, pa, nullptr);
+                    __syncwarp();
+                    continue;
+                }
             }
+            if (!EXACT) continue;
 
             // fused epilogue over the warp's 1024 accumulators
+            const unsigned long long thr = a.thr[q];
             unsigned int *ccnt = a.cand_cnt + q;
             unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
             for (int w = lane; w < kBlockDocs / 4; w += 32) {
@@ -935,20 +1200,18 @@ __global__ void __launch_bounds__(WARPS * 32, MS ? 5 : 6) block_kernel(const __g
         }
     }
     if (lane == 0 && a.stats) {
-        atomicAdd(&a.stats[0], n_units);
-        atomicAdd(&a.stats[1], n_skipped);
-        atomicAdd(&a.stats[2], n_ms);
+        atomicAdd(&a.stats[1], (unsigned long long)n_skipped);
+        atomicAdd(&a.stats[2], (unsigned long long)n_ms);
     }
 }
 
-static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t st) {
+static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, cudaStream_t st) {
     const int n_chunks = (a.n_q + QC - 1) / QC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-    const bool ms = a.split && a.dense_vals != nullptr;
-    const size_t smem = (size_t)BK_WARPS * (ms ? warp_smem_bytes<true>() : warp_smem_bytes<false>());
-    int per_sm = ms ? 5 : 6;
+    const size_t smem = (size_t)BK_WARPS * kBlockDocs * 4;
+    int per_sm = exact ? 6 : BB25_BLOCK_CTAS;
     if (const char *e = getenv("BB25_CTAS_PER_SM")) {
         const int v = atoi(e);
         if (v >= 1 && v <= per_sm) per_sm = v;
@@ -956,7 +1219,7 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, cudaStream_t 
     long long grid = (long long)idx->sm_count * per_sm;
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
-    if (ms) {
+    if (exact) {
         BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         block_kernel<BK_WARPS, true><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
     } else {
@@ -1385,7 +1648,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     const long long route_max = (long long)idx->n_docs / route_div;
     const bool use_cand = use_block_kernel() && idx->prune >= 3 && idx->dense_slot != nullptr && n_q > 0;
     const size_t items_cap = use_cand ? (size_t)n_q * (size_t)(route_max / kCandChunk + 25) : 1;
-    const size_t o_items = align_up(o_listb + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_info = align_up(o_listb + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_items = align_up(o_info + sizeof(longlong2) * nt);
     const size_t o_key = align_up(o_items + sizeof(uint2) * items_cap);
     const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
     if (ensure_workspace(idx, total)) return 1;
@@ -1414,7 +1678,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
 
     BB25_CUDA(cudaMemsetAsync(ws + o_ctr, 0, 128, st));
     prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(q_terms, q_off, n_q, term_base, idx->n_vocab, kth,
-                                                                      d_terms, d_nc, d_thr, d_cnt, d_prev, d_err);
+                                                                      d_terms, d_nc, d_thr, d_cnt, d_prev, d_err,
+                                                                      idx->indptr, idx->dense_vals ? idx->dense_slot : nullptr,
+                                                                      (longlong2 *)(ws + o_info));
     BB25_LAUNCH_CHECK();
 
     // tile groups: a small first group makes a loose threshold seed cheap to repair,
@@ -1454,6 +1720,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.blk_tab = idx->blk_tab;
     ba.n_vocab = idx->n_vocab;
     ba.q_terms = d_terms;
+    ba.qt_info = (const longlong2 *)(ws + o_info);
     ba.q_off = q_off;
     ba.term_base = term_base;
     ba.thr = d_thr;
@@ -1461,8 +1728,10 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.cand_key = d_keys;
     ba.cap = cap;
     ba.prune = idx->prune;
-    ba.split = 0;
-    if (const char *e = getenv("BB25_SPLIT")) ba.split = atoi(e) ? 1 : 0;
+    // first evaluation of a group: order-free sums, candidates re-scored exactly by select_kernel;
+    // threshold repairs after an overflow: query order, exact keys against the 64-bit threshold
+    bool relaxed = idx->dense_vals != nullptr;
+    if (const char *e = getenv("BB25_RELAXED")) relaxed = relaxed && atoi(e) != 0;
     ba.dense_slot = idx->dense_slot;
     ba.dense_vals = idx->dense_vals;
     ba.dense_stride = idx->dense_stride;
@@ -1487,6 +1756,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.out_probs = out_probs;
     sa.n_cand_total = d_ncand;
     sa.tf_search = 1;  // candidate keys carry no matched-term count
+    sa.data = idx->data;
+    sa.rescore = 0;
     sa.indices = idx->indices;
     sa.indptr = idx->indptr;
     sa.blk_tab = idx->blk_tab;
@@ -1501,12 +1772,13 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
 
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
-    const size_t sel_smem = (size_t)cap * 8 + (size_t)kpad * 9 + 260 * 4;
+    const size_t sel_smem = (size_t)cap * 10 + (size_t)kpad * 9 + 260 * 4;  // keys, top, hist+st, flag, rescore list
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     unsigned int *h_flags = (unsigned int *)idx->pinned;  // [0] n_over, [1] err
 
     idx->st_routed = 0;
     idx->st_cand_items = 0;
+    int64_t units_host = 0;  // (block, query) units handed to block_kernel
 
     // ---- candidate-driven queries (pruning level 3) ---------------------------------
     const int32_t *blk_list = nullptr;  // queries left to the block traversal (nullptr = all)
@@ -1635,7 +1907,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
                 ba.n_q = cur_n;
                 ba.blk_begin = bounds[gi];
                 ba.blk_end = bounds[gi + 1];
-                if (launch_block(idx, ba, st)) return 1;
+                if (launch_block(idx, ba, !(relaxed && iter == 0), st)) return 1;
+                units_host += (int64_t)(ba.blk_end - ba.blk_begin) * (int64_t)cur_n;
             } else if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) {
                 return 1;
             }
@@ -1646,6 +1919,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
             idx->st_passes++;
             BB25_CUDA(cudaMemsetAsync(d_nover, 0, sizeof(unsigned int), st));
             sa.q_list = cur_list;
+            sa.rescore = (blockk && relaxed && iter == 0) ? 1 : 0;
             sa.final_pass = (gi == ng - 1) ? 1 : 0;
             sa.over_list = d_list[flip];
             select_kernel<512><<<(unsigned)cur_n, 512, sel_smem, st>>>(sa);
@@ -1669,7 +1943,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     BB25_CUDA(cudaStreamSynchronize(st));
     const unsigned long long *h_c = (const unsigned long long *)idx->pinned;
     idx->st_candidates = (int64_t)h_c[0];
-    idx->st_units = (int64_t)h_c[1];
+    idx->st_units = blockk ? units_host : (int64_t)h_c[1];
     idx->st_units_skipped = (int64_t)h_c[2];
     idx->st_units_maxscore = (int64_t)h_c[3];
     for (int i = 0; i < idx->ev_used; i++) {
