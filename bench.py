@@ -341,7 +341,7 @@ def main():
             "gpu_launches": launches,
             "pruned": {
                 "what": "same batch with the library's default dynamic pruning (bb25_index_set_pruning level %d: "
-                        "block-max skip + MaxScore units + candidate-driven rare-term queries); results bit-identical "
+                        "block-max skip + per-block non-essential frequent terms + candidate-driven rare-term queries); results bit-identical "
                         "to the exhaustive pass" % args.prune_level,
                 "value": args.queries * args.steps / (pr["ms"] / 1000.0), "unit": "queries/s",
                 "ms_per_step": pr["ms"] / args.steps, "kernel_ms_per_step": pr["trav_ms"] / args.steps,

@@ -132,16 +132,17 @@ int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passe
  *   level 0: exhaustive traversal;
  *   level 1: a (block, query) unit whose summed block maxima stay below the query's
  *            current top-k threshold cannot contribute and is skipped;
- *   level 2: additionally, in the remaining units, frequent terms whose block
- *            maxima alone cannot reach the threshold are not traversed: their values
- *            are looked up only for documents another query term touched (MaxScore);
+ *   level 2: additionally, in the remaining units, when the frequent terms' block
+ *            maxima alone cannot reach the threshold, documents matching only those terms
+ *            are not evaluated: the frequent terms' values are added only where another
+ *            query term has a posting (MaxScore's non-essential terms, per block);
  *   level 3 (default): additionally, a query whose threshold exceeds the summed GLOBAL
  *            maxima of its frequent terms leaves the block traversal altogether: only the
  *            postings of its remaining (rare) terms are walked and each such document is
  *            scored completely by one thread (bb25_retrieve_route_stats: how many queries
  *            went that way, and their 1024-posting work items).
  * Results are bit-identical at every level.  bb25_retrieve_prune_stats: units visited /
- * skipped / processed the MaxScore way in the last batch. */
+ * skipped / evaluated with the level-2 restriction in the last batch. */
 int bb25_index_set_pruning(bb25_index *idx, int level);
 int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped,
                               int64_t *units_maxscore);

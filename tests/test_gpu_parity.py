@@ -308,6 +308,53 @@ def test_massive_ties_force_threshold_refinement():
     assert reruns > 0  # at least one candidate row overflowed and was repaired
 
 
+@pytest.mark.parametrize("relaxed", ["1", "0"])
+def test_query_order_sums_survive_order_free_traversal(relaxed, monkeypatch):
+    """The traversal sums frequent terms' dense rows in registers in S-then-D order; bm25s adds in
+    QUERY order.  Here the two orders give different fp32 sums for most documents (query =
+    dense, dense, sparse), and the results must still be the query-order ones bit for bit:
+    select_kernel re-scores every surviving candidate exactly."""
+    pkg = _pkg()
+    from oracle import coracle
+    monkeypatch.setenv("BB25_RELAXED", relaxed)
+    rng = np.random.default_rng(5)
+    n = 8192
+    sparse_docs = np.arange(3, n, 9, dtype=np.int32)            # df < N/8: no dense row
+    v0 = rng.uniform(0.1, 3.0, n).astype(np.float32)            # df = N: dense row
+    v2 = rng.uniform(0.1, 3.0, n).astype(np.float32)
+    v1 = rng.uniform(0.1, 3.0, sparse_docs.size).astype(np.float32)
+    csc = {
+        "data": torch.from_numpy(np.concatenate([v0, v1, v2])),
+        "indices": torch.from_numpy(np.concatenate([np.arange(n, dtype=np.int32), sparse_docs, np.arange(n, dtype=np.int32)])),
+        "indptr": torch.tensor([0, n, n + sparse_docs.size, 2 * n + sparse_docs.size], dtype=torch.int64),
+        "doc_len": torch.from_numpy(rng.integers(5, 60, n).astype(np.int32)),
+        "num_docs": n, "avgdl": 30.0,
+    }
+    in_order = (v0[sparse_docs] + v2[sparse_docs]) + v1         # query [0, 2, 1]
+    s_first = (v1 + v0[sparse_docs]) + v2[sparse_docs]          # what an S-then-D sum gives
+    assert np.count_nonzero(in_order != s_first) > 50           # the orders really differ
+    sc = pkg.BayesianBM25Scorer(alpha=1.3, beta=0.4, base_rate=0.02)
+    sc.index_from_csc(csc)
+    host = _host(csc)
+    params = coracle.make_params(1.3, 0.4, 0.02)
+    flat = np.array([0, 2, 1, 1, 0, 2, 0, 1, 2, 2, 2, 1, 0], dtype=np.int32)
+    off = np.array([0, 3, 6, 9, 13], dtype=np.int64)
+    for level in (0, 3):
+        sc.set_pruning(level)
+        for k in (5, 200, 1500):
+            ids, scores, probs = sc.retrieve_ids(flat, off, k, return_scores=True)
+            o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
+            np.testing.assert_array_equal(ids, o_ids, err_msg=f"level {level} k {k}")
+            np.testing.assert_array_equal(scores.view(np.uint32), o_sc.view(np.uint32))
+            np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
+    # the first query's top documents all hold the sparse term: their scores are the query-order sums
+    ids, scores, _ = sc.retrieve_ids(flat[:3], off[:2], 50, return_scores=True)
+    lookup = dict(zip(sparse_docs.tolist(), in_order.tolist()))
+    for d, s_ in zip(ids[0], scores[0]):
+        if int(d) in lookup:
+            assert np.float32(lookup[int(d)]).view(np.uint32) == np.float32(s_).view(np.uint32)
+
+
 def test_invalid_inputs_are_rejected():
     pkg = _pkg()
     from bayesian_bm25_b200 import _lib, synthetic
