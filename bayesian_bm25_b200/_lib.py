@@ -44,6 +44,7 @@ SIGNATURES = {
     "bb25_index_destroy": (None, [_vp]),
     "bb25_index_info": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32),
                                C.POINTER(_i32), C.POINTER(_i64)]),
+    "bb25_index_table_info": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_get_scores": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bb25_get_probabilities": (_i32, [_vp, _PP, _vp, _i32, _vp, _i64, _vp]),
     "bb25_retrieve_batch": (_i32, [_vp, _PP, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),

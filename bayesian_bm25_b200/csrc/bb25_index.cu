@@ -62,26 +62,93 @@ __global__ void build_tile_table_kernel(const int32_t *__restrict__ indices,
 }
 
 // ---------------------------------------------------------------------------------
-// Block table (see bb25_index::blk_tab).  One CTA walks one term's posting list at a
-// time; entries of empty (block, term) pairs stay {0xFFFFFFFF, 0} -> length 0, never
-// dereferenced.  Pass 0: first-posting offset (min) and block maximum (max of the
-// rounded-up bit pattern; values are >= 0 so bit patterns order like the floats).
-// Pass 1 (after pass 0 finished): posting count into the low 11 bits.
+// Block table (struct BlockTable in bb25_internal.cuh), term-major.
+//   count_term_blocks_kernel   blocks each term touches (-> dense or bitmap form, host decides)
+//   set_block_bits_kernel      bitmap words of the bitmap-form terms
+//   scan_block_bits_kernel     per word: number of the term's entries before it
+//   build_block_table_kernel   pass 0: first-posting offset (min) and block maximum (max of the
+//                              rounded-up bit pattern; values are >= 0 so bit patterns order like
+//                              the floats); pass 1 (after pass 0 finished): posting count into the
+//                              low 11 bits.  Entries are pre-filled with {0xFFFFFFFF, 0}.
+// One CTA walks one term's posting list at a time.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_block_table_kernel(const float *__restrict__ data,
-                                                                const int32_t *__restrict__ indices,
-                                                                const int64_t *__restrict__ indptr,
-                                                                int64_t n_vocab, int pass, uint2 *__restrict__ tab) {
+__global__ void __launch_bounds__(256) count_term_blocks_kernel(const int32_t *__restrict__ indices,
+                                                                const int64_t *__restrict__ indptr, int64_t n_vocab,
+                                                                int32_t *__restrict__ n_touched) {
+    __shared__ int s_cnt;
     for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int64_t s = indptr[t], e = indptr[t + 1];
+        int c = 0;
+        for (int64_t j = s + threadIdx.x; j < e; j += blockDim.x)  // doc ids ascend: count block changes
+            c += (j == s) || (indices[j] / kBlockDocs != indices[j - 1] / kBlockDocs);
+        if (c) atomicAdd(&s_cnt, c);
+        __syncthreads();
+        if (threadIdx.x == 0) n_touched[t] = s_cnt;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) set_block_bits_kernel(const int32_t *__restrict__ indices,
+                                                             const int64_t *__restrict__ indptr, int64_t n_vocab,
+                                                             const longlong2 *__restrict__ row, uint2 *__restrict__ bits) {
+    for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
+        const longlong2 r = row[t];
+        if (r.y < 0) continue;
         const int64_t s = indptr[t], e = indptr[t + 1];
         for (int64_t j = s + threadIdx.x; j < e; j += blockDim.x) {
             const int b = indices[j] / kBlockDocs;
-            uint2 *ent = tab + (size_t)b * (size_t)n_vocab + (size_t)t;
+            atomicOr(&bits[r.y + (b >> 5)].x, 1u << (b & 31));
+        }
+    }
+}
+
+__global__ void scan_block_bits_kernel(int64_t n_vocab, int n_words, const longlong2 *__restrict__ row,
+                                       uint2 *__restrict__ bits) {
+    // one warp per bitmap-form term
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= n_vocab) return;
+    const longlong2 r = row[t];
+    if (r.y < 0) return;
+    unsigned int run = 0;
+    for (int w0 = 0; w0 < n_words; w0 += 32) {
+        const int w = w0 + lane;
+        const unsigned int c = w < n_words ? (unsigned int)__popc(bits[r.y + w].x) : 0u;
+        unsigned int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (w < n_words) bits[r.y + w].y = run + incl - c;
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+}
+
+__device__ __forceinline__ uint2 *tab_slot(uint2 *ent, const uint2 *bits, longlong2 r, int b) {
+    if (r.y < 0) return ent + r.x + b;
+    const uint2 wb = bits[r.y + (b >> 5)];
+    return ent + r.x + wb.y + __popc(wb.x & ((1u << (b & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(256) build_block_table_kernel(const float *__restrict__ data,
+                                                                const int32_t *__restrict__ indices,
+                                                                const int64_t *__restrict__ indptr,
+                                                                int64_t n_vocab, int pass,
+                                                                const longlong2 *__restrict__ row,
+                                                                const uint2 *__restrict__ bits, uint2 *__restrict__ ent_base) {
+    for (int64_t t = blockIdx.x; t < n_vocab; t += gridDim.x) {
+        const int64_t s = indptr[t], e = indptr[t + 1];
+        const longlong2 r = row[t];
+        for (int64_t j = s + threadIdx.x; j < e; j += blockDim.x) {
+            uint2 *ent = tab_slot(ent_base, bits, r, indices[j] / kBlockDocs);
             if (pass == 0) {
                 atomicMin(&ent->x, (unsigned int)(j - s));
-                unsigned int bits = __float_as_uint(data[j]);
-                bits = (bits + kBlkLenMask) & ~kBlkLenMask;  // round the bound up, never down
-                atomicMax(&ent->y, bits);
+                unsigned int v = __float_as_uint(data[j]);
+                v = (v + kBlkLenMask) & ~kBlkLenMask;  // round the bound up, never down
+                atomicMax(&ent->y, v);
             } else {
                 atomicAdd(&ent->y, 1u);
             }
@@ -337,13 +404,54 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
     }
     {
         idx->n_blocks = (int)((n_docs + kBlockDocs - 1) / kBlockDocs);
-        const size_t ne = (size_t)idx->n_blocks * (size_t)n_vocab;
-        TRY(cudaMalloc(&idx->blk_tab, ne * sizeof(uint2)));
-        idx->device_bytes += ne * sizeof(uint2);
-        init_block_table_kernel<<<(unsigned)((ne + 255) / 256), 256>>>(idx->blk_tab, ne);
+        // dense rows for every term while the table fits the budget; otherwise (or with
+        // BB25_TAB_SPARSE=1: wherever smaller, =2: everywhere -- test hooks) the bitmap form
+        const int n_words = (idx->n_blocks + 31) / 32;
         const int grid = (int)(n_vocab < (int64_t)idx->sm_count * 16 ? n_vocab : (int64_t)idx->sm_count * 16);
-        build_block_table_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, 0, idx->blk_tab);
-        build_block_table_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, 1, idx->blk_tab);
+        int32_t *d_touched = nullptr;
+        TRY(cudaMalloc(&d_touched, (size_t)n_vocab * sizeof(int32_t)));
+        count_term_blocks_kernel<<<grid, 256>>>(idx->indices, idx->indptr, n_vocab, d_touched);
+        count_launch();
+        std::vector<int32_t> h_touched((size_t)n_vocab);
+        TRY(cudaMemcpy(h_touched.data(), d_touched, (size_t)n_vocab * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        cudaFree(d_touched);
+        size_t free_b = 0, total_b = 0;
+        TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t dense_bytes = (size_t)idx->n_blocks * (size_t)n_vocab * sizeof(uint2);
+        int sparse_mode = dense_bytes > std::min<size_t>(total_b / 8, free_b / 4) ? 1 : 0;
+        if (const char *e = getenv("BB25_TAB_SPARSE")) sparse_mode = atoi(e);
+        std::vector<longlong2> h_row((size_t)n_vocab);
+        size_t n_ent = 0, n_bits = 0;
+        idx->tab_sparse_terms = 0;
+        for (int64_t t = 0; t < n_vocab; t++) {
+            const size_t sparse_cost = (size_t)n_words + (size_t)h_touched[t];
+            const bool sparse = sparse_mode >= 2 || (sparse_mode == 1 && sparse_cost * 2 < (size_t)idx->n_blocks);
+            h_row[t].x = (long long)n_ent;
+            if (sparse) {
+                h_row[t].y = (long long)n_bits;
+                n_bits += (size_t)n_words;
+                n_ent += (size_t)h_touched[t];
+                idx->tab_sparse_terms++;
+            } else {
+                h_row[t].y = -1;
+                n_ent += (size_t)idx->n_blocks;
+            }
+        }
+        TRY(cudaMalloc(&idx->tab_row, (size_t)n_vocab * sizeof(longlong2)));
+        TRY(cudaMemcpy(idx->tab_row, h_row.data(), (size_t)n_vocab * sizeof(longlong2), cudaMemcpyHostToDevice));
+        TRY(cudaMalloc(&idx->tab_ent, std::max<size_t>(n_ent, 1) * sizeof(uint2)));
+        TRY(cudaMalloc(&idx->tab_bits, std::max<size_t>(n_bits, 1) * sizeof(uint2)));
+        idx->tab_bytes = (size_t)n_vocab * sizeof(longlong2) + (n_ent + n_bits) * sizeof(uint2);
+        idx->device_bytes += idx->tab_bytes;
+        if (n_ent) init_block_table_kernel<<<(unsigned)((n_ent + 255) / 256), 256>>>(idx->tab_ent, n_ent);
+        TRY(cudaMemset(idx->tab_bits, 0, std::max<size_t>(n_bits, 1) * sizeof(uint2)));
+        if (n_bits) {
+            set_block_bits_kernel<<<grid, 256>>>(idx->indices, idx->indptr, n_vocab, idx->tab_row, idx->tab_bits);
+            scan_block_bits_kernel<<<(unsigned)((n_vocab * 32 + 255) / 256), 256>>>(n_vocab, n_words, idx->tab_row, idx->tab_bits);
+            count_launch(2);
+        }
+        build_block_table_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, 0, idx->tab_row, idx->tab_bits, idx->tab_ent);
+        build_block_table_kernel<<<grid, 256>>>(idx->data, idx->indices, idx->indptr, n_vocab, 1, idx->tab_row, idx->tab_bits, idx->tab_ent);
         count_launch(3);
         TRY(cudaGetLastError());
         TRY(cudaDeviceSynchronize());
@@ -409,7 +517,9 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->indptr);
     cudaFree(idx->doc_len);
     cudaFree(idx->tile_off);
-    cudaFree(idx->blk_tab);
+    cudaFree(idx->tab_ent);
+    cudaFree(idx->tab_bits);
+    cudaFree(idx->tab_row);
     cudaFree(idx->dense_slot);
     cudaFree(idx->dense_vals);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
@@ -430,6 +540,13 @@ int bb25_index_info(const bb25_index *idx, int64_t *n_docs, int64_t *n_vocab, in
     if (tile_docs) *tile_docs = idx->tile_docs;
     if (n_tiles) *n_tiles = idx->n_tiles;
     if (device_bytes) *device_bytes = (int64_t)(idx->device_bytes + idx->ws_bytes);
+    return 0;
+}
+
+int bb25_index_table_info(const bb25_index *idx, int64_t *bitmap_terms, int64_t *table_bytes) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (bitmap_terms) *bitmap_terms = idx->tab_sparse_terms;
+    if (table_bytes) *table_bytes = (int64_t)idx->tab_bytes;
     return 0;
 }
 

@@ -192,6 +192,32 @@ __device__ unsigned long long block_kth_largest(const unsigned long long *keys, 
 
 }  // namespace bb25
 
+// Block table: for every (term t, 1024-document block b) that holds postings of t, one entry
+//   .x = offset of the term's first posting in the block, relative to indptr[t]
+//   .y = (fp32 bits of the block maximum, rounded UP to a multiple of 2^11) | posting count (<= 1024)
+// (skip pointer and BlockMaxIndex bound in one 8-byte load; empty pairs read {0xFFFFFFFF, 0}).
+// Term-major.  row[t] = (entry offset, bitmap offset):
+//   bitmap offset < 0   dense row: ent[entry offset + b], one load;
+//   otherwise           the term touches few blocks: bits[bitmap offset + b/32] = (32-block
+//                       bitmap word, number of the term's entries before this word) and the
+//                       entry, if the bit is set, sits at ent[entry offset + prefix + rank in word].
+// Dense rows cost n_blocks x 8 B per term whatever its df, so they are kept only while the whole
+// table fits a budget (every BASELINE configuration); beyond it (million-term vocabularies) the
+// rare terms take the bitmap form: 0.25 B per block plus 8 B per block actually touched.
+struct BlockTable {
+    const uint2 *ent;
+    const uint2 *bits;
+    const longlong2 *row;
+};
+
+__device__ __forceinline__ uint2 tab_lookup(const BlockTable &tb, longlong2 r, int blk) {
+    if (r.y < 0) return tb.ent[r.x + blk];
+    const uint2 wb = tb.bits[r.y + (blk >> 5)];
+    const unsigned bit = 1u << (blk & 31);
+    if (!(wb.x & bit)) return make_uint2(0xFFFFFFFFu, 0u);
+    return tb.ent[r.x + wb.y + __popc(wb.x & (bit - 1u))];
+}
+
 struct bb25_index {
     int device = 0;
     int sm_count = 0;
@@ -204,10 +230,12 @@ struct bb25_index {
     int tile_docs = 0;  // docs per traversal tile (shared-memory accumulator span)
     int n_tiles = 0;
     uint32_t *tile_off = nullptr;  // [n_vocab][n_tiles+1] offsets relative to indptr[t]
-    // block table for the warp-private traversal: [n_blocks][n_vocab] entries
-    //   .x = offset of term t's first posting in block b, relative to indptr[t]
-    //   .y = (fp32 bits of the block maximum, rounded UP to a multiple of 2^11) | posting count (<= 1024)
-    uint2 *blk_tab = nullptr;
+    // block table for the warp-private traversal (struct BlockTable below), term-major
+    uint2 *tab_ent = nullptr;
+    uint2 *tab_bits = nullptr;
+    longlong2 *tab_row = nullptr;
+    int64_t tab_sparse_terms = 0;  // terms kept as bitmap + compact entries
+    size_t tab_bytes = 0;
     int n_blocks = 0;
     int prune = 3;  // 0 exhaustive, 1 block-max skip, 2 + MaxScore units, 3 + candidate-driven queries
     // dense value rows for the most frequent terms (df >= n_docs/8, at most kMaxDenseTerms):

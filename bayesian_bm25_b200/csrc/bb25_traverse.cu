@@ -302,6 +302,7 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
                                     unsigned int *__restrict__ cand_cnt, unsigned int *__restrict__ n_prev,
                                     int *err, const int64_t *__restrict__ indptr = nullptr,
                                     const int32_t *__restrict__ dense_slot = nullptr,
+                                    const longlong2 *__restrict__ tab_row = nullptr,
                                     longlong2 *__restrict__ qt_info = nullptr) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_q) return;
@@ -320,7 +321,10 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
         nocount[i - term_base] = dup ? 1 : 0;
         // per query term: posting-list start and dense-row slot, so that the traversal reads them
         // alongside the term id instead of after it
-        if (qt_info) qt_info[i - term_base] = make_longlong2(indptr[t], dense_slot ? (long long)dense_slot[t] : -1ll);
+        if (qt_info) {
+            qt_info[2 * (i - term_base)] = make_longlong2(indptr[t], dense_slot ? (long long)dense_slot[t] : -1ll);
+            qt_info[2 * (i - term_base) + 1] = tab_row[t];
+        }
         if (kth) {
             uint32_t b = __float_as_uint(kth[t]);
             best = b > best ? b : best;
@@ -363,7 +367,7 @@ struct SelectArgs {
     const float *data;
     const int32_t *indices;
     const int64_t *indptr;
-    const uint2 *blk_tab;
+    BlockTable tab;
     int64_t n_vocab;
     const int32_t *dense_slot;
     const float *dense_vals;
@@ -380,7 +384,7 @@ struct SelectArgs {
 // other terms by binary search inside the document's 1024-doc block slice.
 __device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t doc) {
     const long long t0 = a.q_off[q] - a.term_base, t1 = a.q_off[q + 1] - a.term_base;
-    const uint2 *row = a.blk_tab + (size_t)(doc / (uint32_t)kBlockDocs) * (size_t)a.n_vocab;
+    const int blk = (int)(doc / (uint32_t)kBlockDocs);
     int c = 0;
     for (long long i = t0; i < t1; i++) {
         if (a.q_nocount[i]) continue;  // duplicate occurrence of an earlier term
@@ -390,7 +394,7 @@ __device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t d
             c += (__float_as_uint(a.dense_vals[(size_t)slot * (size_t)a.dense_stride + doc]) != 0x80000000u);
             continue;
         }
-        const uint2 ent = row[t];
+        const uint2 ent = tab_lookup(a.tab, a.tab.row[t], blk);
         const int len = (int)(ent.y & kBlkLenMask);
         if (len == 0) continue;
         long long lo = a.indptr[t] + (long long)ent.x;
@@ -413,7 +417,7 @@ __device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t d
 // +-0.0f, which leaves a non-negative sum unchanged.
 __device__ inline float exact_score_warp(const SelectArgs &a, int q, uint32_t doc, int lane) {
     const long long t0 = a.q_off[q] - a.term_base, t1 = a.q_off[q + 1] - a.term_base;
-    const uint2 *row = a.blk_tab + (size_t)(doc / (uint32_t)kBlockDocs) * (size_t)a.n_vocab;
+    const int blk = (int)(doc / (uint32_t)kBlockDocs);
     float s = 0.f;
     for (long long b0 = t0; b0 < t1; b0 += 32) {
         const int nb = (int)min(32ll, t1 - b0);
@@ -424,7 +428,7 @@ __device__ inline float exact_score_warp(const SelectArgs &a, int q, uint32_t do
             if (slot >= 0) {
                 val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + doc];
             } else {
-                const uint2 ent = row[t];
+                const uint2 ent = tab_lookup(a.tab, a.tab.row[t], blk);
                 const int len = (int)(ent.y & kBlkLenMask);
                 if (len) {
                     long long lo = a.indptr[t] + (long long)ent.x;
@@ -526,12 +530,16 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
             const int sub = lane / g, j = lane % g;
             const int groups = (NT / 32) * (32 / g);
             const int gid = (tid >> 5) * (32 / g) + sub;
-            int t = 0, slot = -1;
+            int slot = -1;
             long long ip = 0;
+            longlong2 trow = make_longlong2(0, -1);
             if (j < m) {
-                t = a.q_terms[t0 + j];
+                const int t = a.q_terms[t0 + j];
                 slot = a.dense_slot ? a.dense_slot[t] : -1;
-                if (slot < 0) ip = a.indptr[t];
+                if (slot < 0) {
+                    ip = a.indptr[t];
+                    trow = a.tab.row[t];
+                }
             }
             for (int base = 0; base < n_list; base += groups) {
                 const bool act = base + gid < n_list;
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
                         if (slot >= 0) {
                             val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + id];
                         } else {
-                            const uint2 ent = a.blk_tab[(size_t)(id / (uint32_t)kBlockDocs) * (size_t)a.n_vocab + t];
+                            const uint2 ent = tab_lookup(a.tab, trow, (int)(id / (uint32_t)kBlockDocs));
                             const int len = (int)(ent.y & kBlkLenMask);
                             if (len) {
                                 long long lo = ip + (long long)ent.x;
@@ -716,16 +724,19 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
 #define BB25_QC 8
 #endif
 constexpr int QC = BB25_QC;  // queries per warp work item
-constexpr int BK_WARPS = 8;  // warps per CTA (4 KB of accumulators per warp)
+#ifndef BB25_BK_WARPS
+#define BB25_BK_WARPS 8
+#endif
+constexpr int BK_WARPS = BB25_BK_WARPS;  // warps per CTA (4 KB of accumulators per warp)
 
 struct BlockArgs {
     const float *data;
     const int32_t *indices;
     const int64_t *indptr;
-    const uint2 *blk_tab;
+    BlockTable tab;
     int64_t n_vocab;
     const int32_t *q_terms;  // sanitised copy, indexed by absolute position - term_base
-    const longlong2 *qt_info;  // per query term: (indptr[t], dense slot or -1)
+    const longlong2 *qt_info;  // per query term, two records: (indptr[t], dense slot or -1), block-table row of t
     const int64_t *q_off;
     int64_t term_base;
     const int32_t *q_list;
@@ -845,16 +856,18 @@ struct TermEnt {
     int dslot;  // dense value row of the term (-1: none, or no posting in this block)
 };
 
-__device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, const uint2 *row, long long pos, bool active) {
+template <bool SPARSE_TAB>
+__device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, int blk, long long pos, bool active) {
     TermEnt e;
     e.start = 0;
     e.len = 0;
     e.bmax = 0.f;
     e.dslot = -1;
     if (active) {
-        const int t = a.q_terms[pos];
-        const longlong2 info = a.qt_info[pos];
-        const uint2 ent = row[t];
+        const longlong2 info = a.qt_info[2 * pos];       // (indptr[t], dense slot)
+        const longlong2 trow = a.qt_info[2 * pos + 1];   // the term's block-table row
+        // SPARSE_TAB = false: the index keeps a dense row for every term (no bitmap branch)
+        const uint2 ent = SPARSE_TAB ? tab_lookup(a.tab, trow, blk) : a.tab.ent[trow.x + blk];
         e.len = (int)(ent.y & kBlkLenMask);
         e.bmax = __uint_as_float(ent.y & ~kBlkLenMask);
         e.start = info.x + (long long)ent.x;
@@ -886,6 +899,10 @@ __device__ __forceinline__ void emit_if_candidate(float v, uint32_t local_id, ui
 #ifndef BB25_PASS_CHUNKS
 #define BB25_PASS_CHUNKS 2
 #endif
+#ifndef BB25_PASS_UNROLL
+#define BB25_PASS_UNROLL 1
+#endif
+constexpr int kPassUnroll = BB25_PASS_UNROLL;
 constexpr int kPassChunks = BB25_PASS_CHUNKS;  // 128-document chunks in flight per round of the order-free pass
 
 // rare path of the order-free pass, kept out of line so it does not cost registers: keys carry
@@ -936,7 +953,7 @@ struct PassArgs {
 template <int ND, bool HAS_S, bool PRED>
 __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassArgs &pa, const float *dbase) {
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
+#pragma unroll kPassUnroll
     for (int h = 0; h < kBlockDocs / (128 * kPassChunks); h++) {
         const int w0 = h * (32 * kPassChunks);
         float4 v[kPassChunks], ra[kPassChunks], rb[kPassChunks];
@@ -986,7 +1003,7 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
 #ifndef BB25_BLOCK_CTAS
 #define BB25_BLOCK_CTAS 4  // resident CTAs per SM of the order-free kernel (register cap 64); measured best
 #endif
-template <int WARPS, bool EXACT>
+template <int WARPS, bool EXACT, bool SPARSE_TAB>
 __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
@@ -1028,10 +1045,9 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
             const int q = __shfl_sync(0xFFFFFFFFu, my_q, sidx);
             const int t0 = __shfl_sync(0xFFFFFFFFu, my_t0, sidx);
             const uint32_t thr_score = __shfl_sync(0xFFFFFFFFu, my_thr_score, sidx);
-            const uint2 *row = a.blk_tab + (size_t)blk * (size_t)a.n_vocab;
 
             if (m <= 32) {
-                const TermEnt e = load_term_entry(a, row, t0 + lane, lane < m);
+                const TermEnt e = load_term_entry<SPARSE_TAB>(a, blk, t0 + lane, lane < m);
                 if (__ballot_sync(0xFFFFFFFFu, e.len > 0) == 0u) continue;  // no posting of any term in this block
                 if (a.prune) {
                     float ub = 0.f;
@@ -1137,7 +1153,7 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
                 unsigned any = 0u;
                 for (int b0 = 0; b0 < m; b0 += 32) {
                     const int nb = min(32, m - b0);
-                    const TermEnt e = load_term_entry(a, row, t0 + b0 + lane, lane < nb);
+                    const TermEnt e = load_term_entry<SPARSE_TAB>(a, blk, t0 + b0 + lane, lane < nb);
                     any |= __ballot_sync(0xFFFFFFFFu, e.len > 0);
                     for (int i = 0; i < nb; i++) ub = __fadd_rn(ub, __shfl_sync(0xFFFFFFFFu, e.bmax, i));
                 }
@@ -1148,7 +1164,7 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
                 }
                 for (int b0 = 0; b0 < m; b0 += 32) {
                     const int nb = min(32, m - b0);
-                    const TermEnt e = load_term_entry(a, row, t0 + b0 + lane, lane < nb);
+                    const TermEnt e = load_term_entry<SPARSE_TAB>(a, blk, t0 + b0 + lane, lane < nb);
                     for (int i = 0; i < nb; i++) {
                         const int len = __shfl_sync(0xFFFFFFFFu, e.len, i);
                         const long long s = shfl_ll(e.start, i);
@@ -1219,13 +1235,21 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     long long grid = (long long)idx->sm_count * per_sm;
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
+    const bool sparse_tab = idx->tab_sparse_terms > 0;
+#define BB25_LAUNCH_BLOCK(EX, SP)                                                                                     \
+    do {                                                                                                              \
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       (int)smem));                                                                   \
+        block_kernel<BK_WARPS, EX, SP><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                               \
+    } while (0)
     if (exact) {
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        block_kernel<BK_WARPS, true><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+        if (sparse_tab) BB25_LAUNCH_BLOCK(true, true);
+        else BB25_LAUNCH_BLOCK(true, false);
     } else {
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        block_kernel<BK_WARPS, false><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);
+        if (sparse_tab) BB25_LAUNCH_BLOCK(false, true);
+        else BB25_LAUNCH_BLOCK(false, false);
     }
+#undef BB25_LAUNCH_BLOCK
     BB25_LAUNCH_CHECK();
     return 0;
 }
@@ -1349,7 +1373,7 @@ struct CandArgs {
     const float *data;
     const int32_t *indices;
     const int64_t *indptr;
-    const uint2 *blk_tab;
+    BlockTable tab;
     int64_t n_vocab;
     const int32_t *dense_slot;
     const float *dense_vals;
@@ -1370,6 +1394,7 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
     __shared__ int s_term[24];
     __shared__ int s_slot[24];
     __shared__ long long s_base[24];
+    __shared__ longlong2 s_row[24];
     __shared__ float s_rest[25];  // s_rest[i] = sum of the global maxima of terms at positions >= i, except `pos`
     const uint2 item = a.items[blockIdx.x];
     const int q = (int)item.x;
@@ -1382,6 +1407,7 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
         s_term[threadIdx.x] = t;
         s_slot[threadIdx.x] = a.dense_slot[t];
         s_base[threadIdx.x] = a.indptr[t];
+        s_row[threadIdx.x] = a.tab.row[t];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1410,7 +1436,6 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
         // MaxScore bound: own value + the other terms' global maxima (1e-5 relative margin
         // for the summation order); tightened term by term as actual values replace maxima
         if (__fmul_rn(__fadd_rn(ve, s_rest[0]), 1.00001f) < thr_val) continue;
-        const uint2 *row = a.blk_tab + (size_t)(d >> 10) * (size_t)a.n_vocab;
         float acc = 0.f;
         bool dup = false;
         for (int i = 0; i < m; i++) {
@@ -1432,7 +1457,7 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
                 val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + d];
                 present = __float_as_uint(val) != 0x80000000u;
             } else {
-                const uint2 ent = row[s_term[i]];
+                const uint2 ent = tab_lookup(a.tab, s_row[i], (int)(d >> 10));
                 const int len = (int)(ent.y & kBlkLenMask);
                 if (len) {
                     long long lo = s_base[i] + (long long)ent.x;
@@ -1649,7 +1674,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     const bool use_cand = use_block_kernel() && idx->prune >= 3 && idx->dense_slot != nullptr && n_q > 0;
     const size_t items_cap = use_cand ? (size_t)n_q * (size_t)(route_max / kCandChunk + 25) : 1;
     const size_t o_info = align_up(o_listb + sizeof(int32_t) * (size_t)n_q);
-    const size_t o_items = align_up(o_info + sizeof(longlong2) * nt);
+    const size_t o_items = align_up(o_info + 2 * sizeof(longlong2) * nt);
     const size_t o_key = align_up(o_items + sizeof(uint2) * items_cap);
     const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
     if (ensure_workspace(idx, total)) return 1;
@@ -1680,7 +1705,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(q_terms, q_off, n_q, term_base, idx->n_vocab, kth,
                                                                       d_terms, d_nc, d_thr, d_cnt, d_prev, d_err,
                                                                       idx->indptr, idx->dense_vals ? idx->dense_slot : nullptr,
-                                                                      (longlong2 *)(ws + o_info));
+                                                                      idx->tab_row, (longlong2 *)(ws + o_info));
     BB25_LAUNCH_CHECK();
 
     // tile groups: a small first group makes a loose threshold seed cheap to repair,
@@ -1717,7 +1742,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.data = idx->data;
     ba.indices = idx->indices;
     ba.indptr = idx->indptr;
-    ba.blk_tab = idx->blk_tab;
+    ba.tab = BlockTable{idx->tab_ent, idx->tab_bits, idx->tab_row};
     ba.n_vocab = idx->n_vocab;
     ba.q_terms = d_terms;
     ba.qt_info = (const longlong2 *)(ws + o_info);
@@ -1760,7 +1785,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.rescore = 0;
     sa.indices = idx->indices;
     sa.indptr = idx->indptr;
-    sa.blk_tab = idx->blk_tab;
+    sa.tab = BlockTable{idx->tab_ent, idx->tab_bits, idx->tab_row};
     sa.n_vocab = idx->n_vocab;
     sa.dense_slot = idx->dense_slot;
     sa.dense_vals = idx->dense_vals;
@@ -1822,7 +1847,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         ca.data = idx->data;
         ca.indices = idx->indices;
         ca.indptr = idx->indptr;
-        ca.blk_tab = idx->blk_tab;
+        ca.tab = BlockTable{idx->tab_ent, idx->tab_bits, idx->tab_row};
         ca.n_vocab = idx->n_vocab;
         ca.dense_slot = idx->dense_slot;
         ca.dense_vals = idx->dense_vals;

@@ -383,6 +383,18 @@ class BayesianBM25Scorer:
         flat = np.concatenate(per_q).astype(np.int32) if per_q and off[-1] > 0 else np.zeros(0, dtype=np.int32)
         return self.retrieve_ids(flat, off, k)
 
+    def index_info(self) -> dict:
+        """Sizes of the device index (bb25_index_info / bb25_index_table_info)."""
+        self._require_index("index_info()")
+        nd, nv, nnz, db = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        td, nt = C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().bb25_index_info(self._handle, C.byref(nd), C.byref(nv), C.byref(nnz), C.byref(td),
+                                              C.byref(nt), C.byref(db)))
+        bt, tb = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().bb25_index_table_info(self._handle, C.byref(bt), C.byref(tb)))
+        return {"n_docs": nd.value, "n_vocab": nv.value, "nnz": nnz.value, "tile_docs": td.value, "n_tiles": nt.value,
+                "device_bytes": db.value, "block_table_bitmap_terms": bt.value, "block_table_bytes": tb.value}
+
     def stats(self) -> dict:
         """Counters of the last batch retrieve (launches, traversal passes, re-runs)."""
         vals = [C.c_int64() for _ in range(4)]

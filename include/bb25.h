@@ -81,6 +81,12 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz,
 void bb25_index_destroy(bb25_index *idx);
 int bb25_index_info(const bb25_index *idx, int64_t *n_docs, int64_t *n_vocab, int64_t *nnz,
                     int *tile_docs, int *n_tiles, int64_t *device_bytes);
+/* The per-(term, 1024-document block) table behind block-max pruning (BlockMaxIndex semantics,
+ * scorer.py:55-99) keeps a dense row per term while that fits a memory budget; for larger
+ * vocabularies the terms that touch few blocks are stored as a bitmap plus compact entries.
+ * bitmap_terms: how many terms took that form; table_bytes: device bytes of the table.
+ * (BB25_TAB_SPARSE=0/1/2 at index creation forces none / wherever smaller / all: test hook.) */
+int bb25_index_table_info(const bb25_index *idx, int64_t *bitmap_terms, int64_t *table_bytes);
 
 /* ---- a1/a4: dense per-query outputs -------------------------------------- */
 

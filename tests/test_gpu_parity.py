@@ -186,24 +186,29 @@ def _queries_with_edge_cases(vocab, seed):
     return flat, off
 
 
-@pytest.mark.parametrize("kernel,tile_docs,prune", [
-    ("block", 8192, 3), ("block", 8192, 2), ("block", 8192, 1), ("block", 8192, 0), ("tile", 8192, 1), ("tile", 16384, 1),
-    ("tile", 32768, 1)])
-def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, monkeypatch):
+@pytest.mark.parametrize("kernel,tile_docs,prune,tab_sparse", [
+    ("block", 8192, 3, "0"), ("block", 8192, 2, "0"), ("block", 8192, 1, "0"), ("block", 8192, 0, "0"),
+    ("block", 8192, 3, "1"), ("block", 8192, 0, "2"), ("block", 8192, 3, "2"),
+    ("tile", 8192, 1, "0"), ("tile", 16384, 1, "0"), ("tile", 32768, 1, "0")])
+def test_retrieve_batch_vs_oracle(kernel, tile_docs, prune, tab_sparse, monkeypatch):
     """Both traversal kernels (warp-private blocks at every pruning level -- exhaustive,
-    block-max skip, block-max skip + MaxScore -- and CTA tiles at every tile size) must
-    give the oracle's result bit for bit."""
+    block-max skip, + frequent-term bound, + candidate-driven queries -- with the block table
+    in its dense, mixed and all-bitmap forms, and CTA tiles at every tile size) must give the
+    oracle's result bit for bit."""
     pkg = _pkg()
     from bayesian_bm25_b200 import synthetic
     from oracle import coracle
     monkeypatch.setenv("BB25_KERNEL", kernel)
     monkeypatch.setenv("BB25_PRUNE", str(prune))
     monkeypatch.setenv("BB25_TILE_DOCS", str(tile_docs))
-    n_docs, vocab = 150_001, 4000
+    monkeypatch.setenv("BB25_TAB_SPARSE", tab_sparse)
+    n_docs, vocab = 150_001, (60_000 if tab_sparse == "1" else 4000)  # rare terms must touch few blocks for the mixed form
     csc = synthetic.zipf_csc(n_docs, vocab, 48.0, seed=21, device=torch.device("cuda:0"))
     host = _host(csc)
     sc = pkg.BayesianBM25Scorer(method="lucene", alpha=2.1, beta=0.3, base_rate=0.03)
     sc.index_from_csc(csc)
+    n_sparse = sc.index_info()["block_table_bitmap_terms"]
+    assert (n_sparse == 0) if tab_sparse == "0" else (n_sparse == vocab if tab_sparse == "2" else 0 < n_sparse < vocab)
     flat, off = _queries_with_edge_cases(vocab, seed=22)
     params = coracle.make_params(2.1, 0.3, 0.03)
     for k in (1, 10, 100, 1000, 4096):
