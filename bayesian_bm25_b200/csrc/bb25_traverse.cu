@@ -364,6 +364,9 @@ struct SelectArgs {
     // rescore != 0: keys [n_prev, n) carry order-free sums (block_kernel's relaxed mode); replace
     // them by the exact query-order score and drop the ones that miss the threshold
     int rescore;
+    // when at most sort_cap (<= kpad) valid keys are left, one bitonic sort replaces the 8-pass radix
+    // select and the separate sort of the winners
+    int sort_cap;
     const float *data;
     const int32_t *indices;
     const int64_t *indptr;
@@ -468,7 +471,8 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int 
 }
 
 // Shared-memory plan of select_kernel: keys u64[cap] | top u64[kpad] | hist u32[256] |
-// st u32[4] | flag u8[kpad] | list u16[cap]   (kpad = k rounded up to a power of two)
+// st u32[4] | flag u8[kpad] | list u16[cap]   (kpad = k rounded up to a power of two; top holds
+// max(kpad, sort_cap) keys)
 template <int NT>
 __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ SelectArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -476,8 +480,8 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
-    unsigned long long *top = keys + a.cap;
-    unsigned int *hist = reinterpret_cast<unsigned int *>(top + kpad);
+    unsigned long long *top = keys + a.cap;  // max(kpad, sort_cap) entries
+    unsigned int *hist = reinterpret_cast<unsigned int *>(top + max(kpad, a.sort_cap));
     unsigned int *st = hist + 256;
     uint8_t *flag = reinterpret_cast<uint8_t *>(st + 4);
     const int tid = threadIdx.x;
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         // scores.  Longer queries were summed in query order already (margin unused).
         uint32_t cut_bits = 0u;
         if (n >= k && m <= 32) {
-            const unsigned long long ta = block_kth_largest<NT>(keys, n, k, hist, st, tid, 4);  // score bits suffice
+            const unsigned long long ta = block_kth_largest<NT>(keys, n, k, hist, st, tid, 3);  // top 24 bits: T rounded down
             cut_bits = __float_as_uint(__fmul_rn(__uint_as_float(key_score_bits(ta)), 0.99997f));
             __syncthreads();
         }
@@ -533,8 +537,10 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
             int slot = -1;
             long long ip = 0;
             longlong2 trow = make_longlong2(0, -1);
+            bool is_dup = false;  // a repeated occurrence of an earlier term does not count twice
             if (j < m) {
                 const int t = a.q_terms[t0 + j];
+                is_dup = a.q_nocount[t0 + j] != 0;
                 slot = a.dense_slot ? a.dense_slot[t] : -1;
                 if (slot < 0) {
                     ip = a.indptr[t];
@@ -546,11 +552,13 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
                 const int i = act ? (int)list[base + gid] : 0;
                 float val = 0.f;
                 uint32_t id = 0;
+                bool present = false;
                 if (act) {
                     id = key_local_id(keys[i]);
                     if (j < m) {
                         if (slot >= 0) {
                             val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + id];
+                            present = __float_as_uint(val) != 0x80000000u;
                         } else {
                             const uint2 ent = tab_lookup(a.tab, trow, (int)(id / (uint32_t)kBlockDocs));
                             const int len = (int)(ent.y & kBlkLenMask);
@@ -563,16 +571,23 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
                                     if ((uint32_t)a.indices[mid] < id) lo = mid + 1;
                                     else hi = mid;
                                 }
-                                if (lo < end && (uint32_t)a.indices[lo] == id) val = a.data[lo];
+                                if (lo < end && (uint32_t)a.indices[lo] == id) {
+                                    val = a.data[lo];
+                                    present = true;
+                                }
                             }
                         }
                     }
                 }
                 float sc = 0.f;
                 for (int u = 0; u < m; u++) sc = __fadd_rn(sc, __shfl_sync(0xFFFFFFFFu, val, sub * g + u));
+                // matched distinct terms (scorer.py:592-601) ride in the key's low bits so that the
+                // output stage need not search again; 0 = not recorded (15 or more: search)
+                const unsigned pres = __ballot_sync(0xFFFFFFFFu, present && !is_dup);
+                const unsigned tfc = (unsigned)__popc(g == 32 ? pres : ((pres >> (sub * g)) & ((1u << g) - 1u)));
                 if (act && j == 0) {
                     const uint32_t bits = __float_as_uint(sc);
-                    unsigned long long key = make_key(bits, id, 0u);
+                    unsigned long long key = make_key(bits, id, tfc < 15u ? tfc : 0u);
                     if (bits == 0u || key < thr64) key = 0ull;
                     keys[i] = key;
                 }
@@ -609,7 +624,24 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         }
     }
     unsigned long long kth = 0ull;
-    if (n_valid >= k) kth = block_kth_largest<NT>(keys, n, k, hist, st, tid);
+    bool sorted = false;  // top[0 .. n_valid) holds every valid key in descending order
+    if (n_valid >= k && n_valid <= a.sort_cap) {
+        int P = 2;
+        while (P < n_valid) P <<= 1;
+        if (tid == 0) st[2] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const unsigned long long key = keys[i];
+            if (key != 0ull) top[atomicAdd(&st[2], 1u)] = key;
+        }
+        for (int i = n_valid + tid; i < P; i += NT) top[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc<NT>(top, P, tid);
+        kth = top[k - 1];
+        sorted = true;
+    } else if (n_valid >= k) {
+        kth = block_kth_largest<NT>(keys, n, k, hist, st, tid);
+    }
 
     if (overflow) {
         // more candidates than the row holds: the k-th best of the stored ones is a
@@ -627,11 +659,15 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     }
     if (!a.final_pass) {
         // keep the best k (order irrelevant), raise the threshold to the k-th key
-        if (tid == 0) st[2] = 0u;
-        __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const unsigned long long key = keys[i];
-            if (key != 0ull && key >= kth) row[atomicAdd(&st[2], 1u)] = key;
+        if (sorted) {
+            for (int i = tid; i < k; i += NT) row[i] = top[i];
+        } else {
+            if (tid == 0) st[2] = 0u;
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) {
+                const unsigned long long key = keys[i];
+                if (key != 0ull && key >= kth) row[atomicAdd(&st[2], 1u)] = key;
+            }
         }
         if (tid == 0) {
             a.cand_cnt[q] = (unsigned int)k;
@@ -643,17 +679,19 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     }
     // final pass: the best min(n, k) keys, sorted
     const int n_pos = min(n_valid, k);
-    if (tid == 0) st[2] = 0u;
-    for (int i = tid; i < kpad; i += NT) top[i] = 0ull;
-    __syncthreads();
-    for (int i = tid; i < n; i += NT) {
-        const unsigned long long key = keys[i];
-        if (key != 0ull && key >= kth) top[atomicAdd(&st[2], 1u)] = key;
+    if (!sorted) {
+        if (tid == 0) st[2] = 0u;
+        for (int i = tid; i < kpad; i += NT) top[i] = 0ull;
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const unsigned long long key = keys[i];
+            if (key != 0ull && key >= kth) top[atomicAdd(&st[2], 1u)] = key;
+        }
+        __syncthreads();
+        int P = 2;
+        while (P < n_pos) P <<= 1;
+        bitonic_sort_desc<NT>(top, P, tid);
     }
-    __syncthreads();
-    int P = 2;
-    while (P < n_pos) P <<= 1;
-    bitonic_sort_desc<NT>(top, P, tid);
     if (tid == 0 && a.n_cand_total) atomicAdd(a.n_cand_total, (unsigned long long)n);
     for (int r = tid; r < n_pos; r += NT) {
         const unsigned long long key = top[r];
@@ -662,7 +700,7 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
         const size_t o = (size_t)q * (size_t)k + r;
         a.out_ids[o] = (int64_t)id + a.doc_id_offset;
         if (a.out_scores) a.out_scores[o] = sc;
-        const int tf = a.tf_search ? count_matched_terms(a, q, id) : (int)key_tf(key);
+        const int tf = (a.tf_search && key_tf(key) == 0u) ? count_matched_terms(a, q, id) : (int)key_tf(key);
         a.out_probs[o] = d_doc_probability(a.params, sc, tf, a.doc_len[id], a.avgdl);
     }
     if (n_pos < k) {
@@ -1715,11 +1753,17 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     int ng = 0;
     const int T = blockk ? idx->n_blocks : idx->n_tiles;
     bounds[0] = 0;
-    if (T >= 16) {
+    int want_groups = 3;
+    if (const char *e = getenv("BB25_GROUPS")) want_groups = atoi(e);  // tuning: 1, 2 or 3 block groups
+    if (T >= 16 && want_groups >= 3) {
         bounds[1] = std::max(1, T / 16);
         bounds[2] = std::max(bounds[1] + 1, T / 4);
         bounds[3] = T;
         ng = 3;
+    } else if (T >= 16 && want_groups == 2) {
+        bounds[1] = std::max(1, T / 8);
+        bounds[2] = T;
+        ng = 2;
     } else {
         bounds[1] = T;
         ng = 1;
@@ -1797,6 +1841,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
 
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
+    // at most kpad valid keys left (the usual case after the re-scoring pre-filter): one bitonic sort
+    // replaces the 8-pass radix select plus the sort of the winners; more keys: radix select first
+    sa.sort_cap = kpad;
     const size_t sel_smem = (size_t)cap * 10 + (size_t)kpad * 9 + 260 * 4;  // keys, top, hist+st, flag, rescore list
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     unsigned int *h_flags = (unsigned int *)idx->pinned;  // [0] n_over, [1] err
