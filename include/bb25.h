@@ -116,6 +116,9 @@ int bb25_get_probabilities(bb25_index *idx, const bb25_params *params, const int
  *   q_off[Q+1]         int64 offsets                                            (dev)
  *   out_ids[Q*k] int64, out_scores[Q*k] fp32 (may be NULL), out_probs[Q*k] fp64 (dev)
  * Requires 1 <= k <= min(n_docs, 4096).  Synchronises `stream` before returning.
+ * Scores are bm25s's fp32 sums bit for bit (terms added in query order): the
+ * traversal may sum in another order to find candidates, but every candidate is
+ * re-scored in query order before it is ranked.
  */
 int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
                         const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,

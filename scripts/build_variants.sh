@@ -1,6 +1,6 @@
 #!/bin/bash
 # Tuning builds of libbb25 (not shipped): scripts/build_variants.sh "<name>:<nvcc -D flags>" ...
-# e.g. scripts/build_variants.sh "c5k2:-DBB25_MS_CTAS=5 -DBB25_SPLIT_CHUNKS=2"
+# e.g. scripts/build_variants.sh "c5k1:-DBB25_BLOCK_CTAS=5 -DBB25_PASS_CHUNKS=1" "qc16:-DBB25_QC=16"
 cd "$(dirname "$0")/.."
 mkdir -p build_variants
 for spec in "$@"; do
