@@ -237,10 +237,11 @@ struct bb25_index {
     int64_t tab_sparse_terms = 0;  // terms kept as bitmap + compact entries
     size_t tab_bytes = 0;
     int n_blocks = 0;
-    int prune = 3;  // 0 exhaustive, 1 block-max skip, 2 + MaxScore units, 3 + candidate-driven queries
+    int prune = 3;  // 0 exhaustive, 1 block-max skip, 2 + frequent-term bound per block, 3 + candidate-driven queries
     // dense value rows for the most frequent terms (df >= n_docs/8, at most kMaxDenseTerms):
     // dense_vals[slot][doc] = posting value, or -0.0f where absent; O(1) lookup of a head term's
-    // contribution to one document, used by the MaxScore path of the block kernel
+    // contribution to one document (exact re-scoring, candidate path, tf recovery), and the rows the
+    // order-free traversal pass streams 128 bits per lane
     int32_t *dense_slot = nullptr;  // [n_vocab] slot or -1
     float *dense_vals = nullptr;    // [n_dense][dense_stride]
     int n_dense = 0;
@@ -255,7 +256,7 @@ struct bb25_index {
     // stats of the last retrieve_batch
     int64_t st_launches = 0, st_passes = 0, st_reruns = 0, st_candidates = 0;
     int64_t st_routed = 0, st_cand_items = 0;  // queries evaluated candidate-by-candidate / their work items
-    int64_t st_units = 0, st_units_skipped = 0, st_units_maxscore = 0;  // (block, query) units visited / pruned / MaxScore
+    int64_t st_units = 0, st_units_skipped = 0, st_units_maxscore = 0;  // (block, query) units visited / pruned / evaluated with the level-2 restriction
     // CUDA-event pairs around the traversal launches of the last retrieve_batch
     static constexpr int kMaxEv = 256;
     cudaEvent_t ev[2 * kMaxEv] = {};

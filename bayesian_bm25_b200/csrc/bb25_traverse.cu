@@ -789,7 +789,7 @@ struct BlockArgs {
     const float *dense_vals;
     int64_t dense_stride;
     unsigned long long *work_counter;
-    unsigned long long *stats;  // [0] units visited, [1] pruned by the block-max bound, [2] MaxScore units
+    unsigned long long *stats;  // [1] units pruned by the block-max bound, [2] units under the level-2 restriction
 };
 
 // per-warp shared memory: 1024 fp32 accumulators

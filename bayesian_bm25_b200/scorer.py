@@ -413,7 +413,9 @@ class BayesianBM25Scorer:
 
     def set_pruning(self, level: int) -> None:
         """Dynamic pruning level of batch retrieve: 0 exhaustive, 1 block-max skip,
-        2 + MaxScore units, 3 + candidate-driven evaluation of rare-term queries (default).
+        2 + per-block non-essential frequent terms (documents matching only them are not evaluated when
+        their summed block maxima cannot reach the threshold; counted as "units_maxscore" in stats()),
+        3 + candidate-driven evaluation of rare-term queries (default).
         Results are identical at every level."""
         self._require_index("set_pruning()")
         _lib.check(_lib.lib().bb25_index_set_pruning(self._handle, int(level)))
