@@ -1038,22 +1038,32 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
     }
 }
 
+// Resident CTAs per SM (= register cap) of the order-free kernel, measured on config 2: the exhaustive
+// pass likes 5 x 8 warps at 48 registers (61.0 vs 62.5 ms per step), the pruned passes, whose units are
+// fewer and heavier, 4 x 8 warps at 64 registers (39.7 vs 40.7 ms).  The query-order kernel runs 6.
 #ifndef BB25_BLOCK_CTAS
-#define BB25_BLOCK_CTAS 4  // resident CTAs per SM of the order-free kernel (register cap 64); measured best
+#define BB25_BLOCK_CTAS 5
 #endif
-template <int WARPS, bool EXACT, bool SPARSE_TAB>
-__global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block_kernel(const __grid_constant__ BlockArgs a) {
+#ifndef BB25_BLOCK_CTAS_PRUNED
+#define BB25_BLOCK_CTAS_PRUNED 4
+#endif
+template <int WARPS, bool EXACT, bool SPARSE_TAB, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float *acc = reinterpret_cast<float *>(smem + (size_t)warp * (kBlockDocs * 4));
     float4 *acc4 = reinterpret_cast<float4 *>(acc);
+    // per warp: QC query descriptors (q, term count, first term position, threshold score bits) and one
+    // slot of counters ([0] units pruned by the block-max bound, [1] units under the level-2 restriction)
+    uint4 *sdesc = reinterpret_cast<uint4 *>(smem + (size_t)WARPS * (kBlockDocs * 4)) + warp * (QC + 1);
+    unsigned int *scnt = reinterpret_cast<unsigned int *>(sdesc + QC);
     for (int i = lane; i < kBlockDocs / 4; i += 32) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 4) scnt[lane] = 0u;
     __syncwarp();
 
     const int n_chunks = (a.n_q + QC - 1) / QC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
-    unsigned int n_skipped = 0, n_ms = 0;  // per warp and launch: far below 2^32
 
     for (;;) {
         long long item = 0;
@@ -1065,24 +1075,26 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
         const int nslots = min(QC, a.n_q - slot0);
         const int doc_base = blk * kBlockDocs;
 
-        // lane s holds the description of the chunk's s-th query (the full 64-bit threshold is
-        // re-read by the query-order path, which alone needs it)
-        int my_q = 0, my_m = 0, my_t0 = 0;
-        uint32_t my_thr_score = 0;
+        // the descriptions of the chunk's queries are fetched by lanes 0..nslots-1 in one round and
+        // parked in shared memory (registers are what limits the kernel's occupancy); the full 64-bit
+        // threshold is re-read by the query-order path, which alone needs it
+        __syncwarp();
         if (lane < nslots) {
-            my_q = a.q_list ? a.q_list[slot0 + lane] : slot0 + lane;
+            const int my_q = a.q_list ? a.q_list[slot0 + lane] : slot0 + lane;
             const long long t0 = a.q_off[my_q];
-            my_m = (int)max(0ll, (long long)a.q_off[my_q + 1] - t0);
-            my_t0 = (int)(t0 - a.term_base);
-            my_thr_score = (uint32_t)(a.thr[my_q] >> 33);
+            const int my_m = (int)max(0ll, (long long)a.q_off[my_q + 1] - t0);
+            sdesc[lane] = make_uint4((unsigned)my_q, (unsigned)my_m, (unsigned)(int)(t0 - a.term_base),
+                                     (uint32_t)(a.thr[my_q] >> 33));
         }
+        __syncwarp();
 
         for (int sidx = 0; sidx < nslots; sidx++) {
-            const int m = __shfl_sync(0xFFFFFFFFu, my_m, sidx);
+            const uint4 desc = sdesc[sidx];
+            const int m = (int)desc.y;
             if (m == 0) continue;
-            const int q = __shfl_sync(0xFFFFFFFFu, my_q, sidx);
-            const int t0 = __shfl_sync(0xFFFFFFFFu, my_t0, sidx);
-            const uint32_t thr_score = __shfl_sync(0xFFFFFFFFu, my_thr_score, sidx);
+            const int q = (int)desc.x;
+            const int t0 = (int)desc.z;
+            const uint32_t thr_score = desc.w;
 
             if (m <= 32) {
                 const TermEnt e = load_term_entry<SPARSE_TAB>(a, blk, t0 + lane, lane < m);
@@ -1091,7 +1103,7 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
                     float ub = 0.f;
                     for (int i = 0; i < m; i++) ub = __fadd_rn(ub, __shfl_sync(0xFFFFFFFFu, e.bmax, i));
                     if (__float_as_uint(ub) < thr_score) {
-                        n_skipped++;
+                        if (lane == 0) scnt[0]++;
                         continue;
                     }
                 }
@@ -1129,7 +1141,7 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
                             dub = __fadd_rn(dub, __shfl_sync(0xFFFFFFFFu, e.bmax, __ffs(mm) - 1));
                         if (__float_as_uint(dub) < thr_score) {
                             dense_all = false;
-                            n_ms++;
+                            if (lane == 0) scnt[1]++;
                         }
                     }
                     if (!smask && !dense_all) continue;
@@ -1197,7 +1209,7 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
                 }
                 if (any == 0u) continue;
                 if (a.prune && __float_as_uint(ub) < thr_score) {
-                    n_skipped++;
+                    if (lane == 0) scnt[0]++;
                     continue;
                 }
                 for (int b0 = 0; b0 < m; b0 += 32) {
@@ -1254,8 +1266,8 @@ __global__ void __launch_bounds__(WARPS * 32, EXACT ? 6 : BB25_BLOCK_CTAS) block
         }
     }
     if (lane == 0 && a.stats) {
-        atomicAdd(&a.stats[1], (unsigned long long)n_skipped);
-        atomicAdd(&a.stats[2], (unsigned long long)n_ms);
+        atomicAdd(&a.stats[1], (unsigned long long)scnt[0]);
+        atomicAdd(&a.stats[2], (unsigned long long)scnt[1]);
     }
 }
 
@@ -1264,8 +1276,9 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-    const size_t smem = (size_t)BK_WARPS * kBlockDocs * 4;
-    int per_sm = exact ? 6 : BB25_BLOCK_CTAS;
+    const size_t smem = (size_t)BK_WARPS * (kBlockDocs * 4 + (QC + 1) * sizeof(uint4));
+    const bool pruned_cfg = a.prune != 0;
+    int per_sm = exact ? 6 : (pruned_cfg ? BB25_BLOCK_CTAS_PRUNED : BB25_BLOCK_CTAS);
     if (const char *e = getenv("BB25_CTAS_PER_SM")) {
         const int v = atoi(e);
         if (v >= 1 && v <= per_sm) per_sm = v;
@@ -1274,18 +1287,21 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
     const bool sparse_tab = idx->tab_sparse_terms > 0;
-#define BB25_LAUNCH_BLOCK(EX, SP)                                                                                     \
+#define BB25_LAUNCH_BLOCK(EX, SP, CT)                                                                                 \
     do {                                                                                                              \
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                       (int)smem));                                                                   \
-        block_kernel<BK_WARPS, EX, SP><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                               \
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP, CT>,                                            \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        block_kernel<BK_WARPS, EX, SP, CT><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                           \
     } while (0)
     if (exact) {
-        if (sparse_tab) BB25_LAUNCH_BLOCK(true, true);
-        else BB25_LAUNCH_BLOCK(true, false);
+        if (sparse_tab) BB25_LAUNCH_BLOCK(true, true, 6);
+        else BB25_LAUNCH_BLOCK(true, false, 6);
+    } else if (pruned_cfg) {
+        if (sparse_tab) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS_PRUNED);
+        else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS_PRUNED);
     } else {
-        if (sparse_tab) BB25_LAUNCH_BLOCK(false, true);
-        else BB25_LAUNCH_BLOCK(false, false);
+        if (sparse_tab) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS);
+        else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS);
     }
 #undef BB25_LAUNCH_BLOCK
     BB25_LAUNCH_CHECK();
