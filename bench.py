@@ -352,7 +352,7 @@ def main():
                 "candidate_items_per_step": pr["candidate_items"],
             },
             "roofline": {
-                "bound": "hbm", "kernel": "bb25::block_kernel (posting traversal + fused epilogue, exhaustive)",
+                "bound": "hbm", "kernel": "bb25::block_kernel (order-free posting traversal, exhaustive; candidates re-scored in query order by select_kernel)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": ncu_traffic_per_launch(),
                 "algorithmic_bytes_per_step_per_gpu": alg_bytes_gpu,
