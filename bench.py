@@ -359,7 +359,8 @@ def main():
                 "kernel_ms_per_step": trav_ms_max / args.steps, "kernel_launches_per_step": trav_launches / args.steps,
                 "note": "achieved = sum_q sum_t df(t)*8B (+k*20B) / summed traversal-kernel time (CUDA events in libbb25); "
                         "all warps share a block's index slice through L2, so DRAM traffic is far below the algorithmic "
-                        "bytes and the figure can exceed the HBM peak (DESIGN.md 4.1)",
+                        "bytes and the figure can exceed the HBM peak (DESIGN.md 4.1); the exact re-scoring of the "
+                        "emitted candidates runs in select_kernel and is part of ms_per_step, not of this kernel time",
             },
         }
         if host_csc is not None:
