@@ -40,6 +40,7 @@ SIGNATURES = {
     "bb25_version": (_i32, []),
     "bb25_launch_count": (C.c_ulonglong, []),
     "bb25_device_count": (_i32, []),
+    "bb25_measure_read_bandwidth": (_i32, [_i32, _i64, _i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "bb25_index_create": (_i32, [_i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _dbl, _i64, C.POINTER(_vp)]),
     "bb25_index_destroy": (None, [_vp]),
     "bb25_index_info": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32),
@@ -48,7 +49,11 @@ SIGNATURES = {
     "bb25_get_scores": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bb25_get_probabilities": (_i32, [_vp, _PP, _vp, _i32, _vp, _i64, _vp]),
     "bb25_retrieve_batch": (_i32, [_vp, _PP, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "bb25_retrieve_batch_ex": (_i32, [_vp, _PP, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bb25_retrieve_batch_host": (_i32, [_vp, _PP, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "bb25_retrieve_one_dense": (_i32, [_vp, _PP, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "bb25_retrieve_sync_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "bb25_index_set_threshold_exchange": (_i32, [_vp, _vp, _vp]),
     "bb25_retrieve_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_index_set_pruning": (_i32, [_vp, _i32]),
     "bb25_retrieve_prune_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

@@ -286,6 +286,18 @@ int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out) {
         return 0;
     }
     float *buf = nullptr;
+    if (idx->kth_cache.size() >= 8) {
+        // bounded cache: drop the entry for the largest k other than 1 (k = 1 holds the global term maxima)
+        auto victim = idx->kth_cache.end();
+        for (auto jt = idx->kth_cache.begin(); jt != idx->kth_cache.end(); ++jt)
+            if (jt->first != 1) victim = jt;
+        if (victim != idx->kth_cache.end()) {
+            BB25_CUDA(cudaStreamSynchronize(st));
+            cudaFree(victim->second);
+            idx->kth_cache.erase(victim);
+            idx->device_bytes -= sizeof(float) * (size_t)idx->n_vocab;
+        }
+    }
     BB25_CUDA(cudaMalloc(&buf, sizeof(float) * (size_t)idx->n_vocab));
     idx->device_bytes += sizeof(float) * (size_t)idx->n_vocab;
     int grid = (int)(idx->n_vocab < (int64_t)idx->sm_count * 8 ? idx->n_vocab : (int64_t)idx->sm_count * 8);
@@ -524,6 +536,9 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->dense_vals);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
     if (idx->ws) cudaFree(idx->ws);
+    if (idx->hs_dev) cudaFree(idx->hs_dev);
+    if (idx->hs_stream) cudaStreamDestroy(idx->hs_stream);
+    if (idx->ws_ev) cudaEventDestroy(idx->ws_ev);
     if (idx->pinned) cudaFreeHost(idx->pinned);
     for (int i = 0; i < idx->n_ev; i++) cudaEventDestroy(idx->ev[i]);
     if (prev >= 0) cudaSetDevice(prev);

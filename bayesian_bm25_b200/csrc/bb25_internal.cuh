@@ -264,9 +264,32 @@ struct bb25_index {
     int ev_used = 0;    // pairs recorded in the last call
     double st_traverse_ms = 0.0;
     int64_t st_traverse_launches = 0;
+    int64_t st_syncs = 0;           // host synchronisations inside the last retrieve_batch
+    int64_t st_bad = 0;             // queries that needed the host-driven repair / ...
+    int64_t st_dense_fallback = 0;  // ... the dense guaranteed path
+    // device + stream of the host-buffer entry points (grow-only, reused across calls)
+    void *hs_dev = nullptr;
+    size_t hs_bytes = 0;
+    cudaStream_t hs_stream = nullptr;
+    // last use of the shared workspace: calls on another stream wait for it before touching the workspace
+    cudaEvent_t ws_ev = nullptr;
+    // sharded retrieval: called between block groups so that the ranks can agree on tighter thresholds
+    bb25_exchange_fn exchange_cb = nullptr;
+    void *exchange_user = nullptr;
 };
 
 namespace bb25 {
+// stream-order the shared workspace across streams: acquire before the first use in a call, release after the last
+inline void ws_acquire(bb25_index *idx, cudaStream_t st) {
+    if (idx->ws_ev) cudaStreamWaitEvent(st, idx->ws_ev, 0);
+}
+inline void ws_release(bb25_index *idx, cudaStream_t st) {
+    if (!idx->ws_ev && cudaEventCreateWithFlags(&idx->ws_ev, cudaEventDisableTiming) != cudaSuccess) {
+        idx->ws_ev = nullptr;
+        return;
+    }
+    cudaEventRecord(idx->ws_ev, st);
+}
 int ensure_workspace(bb25_index *idx, size_t bytes);
 int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out);
 }  // namespace bb25

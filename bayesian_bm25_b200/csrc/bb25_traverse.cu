@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "bb25_internal.cuh"
 
@@ -41,6 +42,7 @@ struct TileArgs {
     int64_t term_base;
     const int32_t *q_list;  // NULL = queries [0, n_q)
     int n_q;
+    const unsigned int *n_q_ptr;  // when set, the number of queries is read on the device (no host round trip)
     int tile_begin, tile_end;
     const unsigned long long *thr;
     unsigned int *cand_cnt;
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE>()) tile_kernel(const 
     if (HAS_CNT)
         for (int i = tid; i < D / 16; i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
 
-    const int n_chunks = (a.n_q + QB - 1) / QB;
+    const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
+    const int n_chunks = (n_q + QB - 1) / QB;
     const long long n_items = (long long)(a.tile_end - a.tile_begin) * n_chunks;
 
     for (;;) {
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE>()) tile_kernel(const 
         if (item >= n_items) break;
         const int tile = a.tile_begin + (int)(item / n_chunks);
         const int slot0 = (int)(item % n_chunks) * QB;
-        const int nslots = min(QB, a.n_q - slot0);
+        const int nslots = min(QB, n_q - slot0);
         const int doc_base = tile * D;
 
         if (tid < nslots) {
@@ -296,9 +299,10 @@ __global__ void __launch_bounds__(NT, ctas_per_sm<D, MODE>()) tile_kernel(const 
 // per-query preparation: sanitised term copy, duplicate flags, threshold seed
 // ---------------------------------------------------------------------------------
 __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const int64_t *__restrict__ q_off,
-                                    int64_t n_q, int64_t term_base, int64_t n_vocab,
+                                    int64_t n_q, int64_t term_base, int64_t n_terms_total, int64_t n_vocab,
                                     const float *__restrict__ kth, int32_t *__restrict__ qt_ws,
-                                    uint8_t *__restrict__ nocount, unsigned long long *__restrict__ thr,
+                                    uint8_t *__restrict__ nocount, int64_t *__restrict__ qo_ws,
+                                    unsigned long long *__restrict__ thr,
                                     unsigned int *__restrict__ cand_cnt, unsigned int *__restrict__ n_prev,
                                     int *err, const int64_t *__restrict__ indptr = nullptr,
                                     const int32_t *__restrict__ dense_slot = nullptr,
@@ -306,24 +310,32 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
                                     longlong2 *__restrict__ qt_info = nullptr) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_q) return;
-    const int64_t t0 = q_off[q], t1 = q_off[q + 1];
-    if (t1 < t0) { atomicOr(err, 2); }
+    // Offsets are rebased to the batch's first term and clamped into [0, n_terms_total]: whatever
+    // q_off holds, no later kernel can index outside the n_terms_total-entry workspaces.  A query
+    // whose range was clamped or runs backwards is flagged (the call fails) and treated as empty.
+    const int64_t r0 = q_off[q] - term_base, r1 = q_off[q + 1] - term_base;
+    const int64_t t0 = r0 < 0 ? 0 : (r0 > n_terms_total ? n_terms_total : r0);
+    int64_t t1 = r1 < 0 ? 0 : (r1 > n_terms_total ? n_terms_total : r1);
+    if (t0 != r0 || t1 != r1 || t1 < t0) atomicOr(err, 2);
+    qo_ws[q] = t0;
+    if (q == n_q - 1) qo_ws[n_q] = t1;
+    if (t1 < t0) t1 = t0;
     uint32_t best = 0;
     for (int64_t i = t0; i < t1; i++) {
-        int32_t t = q_terms[i];
+        int32_t t = q_terms[term_base + i];
         if (t < 0 || (int64_t)t >= n_vocab) {
             atomicOr(err, 1);
             t = 0;
         }
         bool dup = false;
-        for (int64_t j = t0; j < i && !dup; j++) dup = (q_terms[j] == t);
-        qt_ws[i - term_base] = t;
-        nocount[i - term_base] = dup ? 1 : 0;
+        for (int64_t j = t0; j < i && !dup; j++) dup = (q_terms[term_base + j] == t);
+        qt_ws[i] = t;
+        nocount[i] = dup ? 1 : 0;
         // per query term: posting-list start and dense-row slot, so that the traversal reads them
         // alongside the term id instead of after it
         if (qt_info) {
-            qt_info[2 * (i - term_base)] = make_longlong2(indptr[t], dense_slot ? (long long)dense_slot[t] : -1ll);
-            qt_info[2 * (i - term_base) + 1] = tab_row[t];
+            qt_info[2 * i] = make_longlong2(indptr[t], dense_slot ? (long long)dense_slot[t] : -1ll);
+            qt_info[2 * i + 1] = tab_row[t];
         }
         if (kth) {
             uint32_t b = __float_as_uint(kth[t]);
@@ -343,6 +355,8 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
 // ---------------------------------------------------------------------------------
 struct SelectArgs {
     const int32_t *q_list;
+    int n_list;                      // number of queries to process (host-side count) ...
+    const unsigned int *n_list_ptr;  // ... or, when set, read on the device
     unsigned int *cand_cnt;
     unsigned int *n_prev;
     unsigned long long *cand_key;
@@ -474,8 +488,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *keys, int 
 // st u32[4] | flag u8[kpad] | list u16[cap]   (kpad = k rounded up to a power of two; top holds
 // max(kpad, sort_cap) keys)
 template <int NT>
-__global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ SelectArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void select_one(const SelectArgs &a, unsigned char *smem, const int q) {
     const int k = a.k;
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
@@ -485,7 +498,6 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     unsigned int *st = hist + 256;
     uint8_t *flag = reinterpret_cast<uint8_t *>(st + 4);
     const int tid = threadIdx.x;
-    const int q = a.q_list ? a.q_list[blockIdx.x] : (int)blockIdx.x;
     const unsigned int n_raw = a.cand_cnt[q];
     const int n = (int)min(n_raw, (unsigned)a.cap);
     unsigned long long *row = a.cand_key + (size_t)q * (size_t)a.cap;
@@ -733,6 +745,19 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
     }
 }
 
+// One CTA per query of the list, grid-strided: the list length may live on the device (repair
+// rounds are launched without knowing how many queries overflowed), in which case the grid is a
+// small fixed size and CTAs without work leave at once.
+template <int NT>
+__global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ SelectArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const unsigned int n_list = a.n_list_ptr ? *a.n_list_ptr : (unsigned int)a.n_list;
+    for (unsigned int b = blockIdx.x; b < n_list; b += gridDim.x) {
+        select_one<NT>(a, smem, a.q_list ? a.q_list[b] : (int)b);
+        __syncthreads();
+    }
+}
+
 // =================================================================================
 // Warp-private traversal (retrieve mode).  A BLOCK = 1024 consecutive documents whose
 // fp32 accumulators (4 KB) belong to ONE warp; a warp pulls (block, 8-query chunk)
@@ -779,6 +804,7 @@ struct BlockArgs {
     int64_t term_base;
     const int32_t *q_list;
     int n_q;
+    const unsigned int *n_q_ptr;  // when set, the number of queries is read on the device
     int blk_begin, blk_end;
     const unsigned long long *thr;
     unsigned int *cand_cnt;
@@ -789,7 +815,7 @@ struct BlockArgs {
     const float *dense_vals;
     int64_t dense_stride;
     unsigned long long *work_counter;
-    unsigned long long *stats;  // [1] units pruned by the block-max bound, [2] units under the level-2 restriction
+    unsigned long long *stats;  // [0] (block, query) units handed out, [1] units pruned by the block-max bound, [2] units under the level-2 restriction
 };
 
 // per-warp shared memory: 1024 fp32 accumulators
@@ -1062,8 +1088,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
     if (lane < 4) scnt[lane] = 0u;
     __syncwarp();
 
-    const int n_chunks = (a.n_q + QC - 1) / QC;
+    const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
+    const int n_chunks = (n_q + QC - 1) / QC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
+    if (a.stats && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
 
     for (;;) {
         long long item = 0;
@@ -1072,7 +1101,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
         if (item >= n_items) break;
         const int blk = a.blk_begin + (int)(item / n_chunks);
         const int slot0 = (int)(item % n_chunks) * QC;
-        const int nslots = min(QC, a.n_q - slot0);
+        const int nslots = min(QC, n_q - slot0);
         const int doc_base = blk * kBlockDocs;
 
         // the descriptions of the chunk's queries are fetched by lanes 0..nslots-1 in one round and
@@ -1272,7 +1301,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
 }
 
 static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, cudaStream_t st) {
-    const int n_chunks = (a.n_q + QC - 1) / QC;
+    const int n_chunks = (a.n_q + QC - 1) / QC;  // a.n_q: host-side upper bound of the query count
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (n_items <= 0) return 0;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
@@ -1411,9 +1440,9 @@ __global__ void route_kernel(const RouteArgs a) {
 }
 
 // work items again for routed queries whose candidate row overflowed
-__global__ void rebuild_items_kernel(const RouteArgs a, const int32_t *list, int n_list) {
+__global__ void rebuild_items_kernel(const RouteArgs a, const int32_t *list, const unsigned int *n_list) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_list) return;
+    if (idx >= (int)*n_list) return;
     const int q = list[idx];
     const long long t0 = a.q_off[q] - a.term_base;
     const int m = (int)(a.q_off[q + 1] - a.q_off[q]);
@@ -1437,6 +1466,7 @@ struct CandArgs {
     int64_t term_base;
     const uint32_t *ne_mask;
     const uint2 *items;
+    const unsigned int *n_items;  // device-side number of work items
     const unsigned long long *thr;
     unsigned int *cand_cnt;
     unsigned long long *cand_key;
@@ -1450,93 +1480,97 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
     __shared__ long long s_base[24];
     __shared__ longlong2 s_row[24];
     __shared__ float s_rest[25];  // s_rest[i] = sum of the global maxima of terms at positions >= i, except `pos`
-    const uint2 item = a.items[blockIdx.x];
-    const int q = (int)item.x;
-    const int pos = (int)(item.y >> 24);
-    const unsigned int chunk = item.y & 0xFFFFFFu;
-    const long long t0 = a.q_off[q] - a.term_base;
-    const int m = (int)(a.q_off[q + 1] - a.q_off[q]);
-    if (threadIdx.x < m) {
-        const int t = a.q_terms[t0 + threadIdx.x];
-        s_term[threadIdx.x] = t;
-        s_slot[threadIdx.x] = a.dense_slot[t];
-        s_base[threadIdx.x] = a.indptr[t];
-        s_row[threadIdx.x] = a.tab.row[t];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float r = 0.f;
-        s_rest[m] = 0.f;
-        for (int i = m - 1; i >= 0; i--) {
-            if (i != pos) r = __fadd_rn(r, a.gmax[s_term[i]]);
-            s_rest[i] = r;
+    const unsigned int n_items = *a.n_items;
+    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        __syncthreads();  // the previous item's shared descriptors are no longer read
+        const uint2 item = a.items[it];
+        const int q = (int)item.x;
+        const int pos = (int)(item.y >> 24);
+        const unsigned int chunk = item.y & 0xFFFFFFu;
+        const long long t0 = a.q_off[q] - a.term_base;
+        const int m = (int)(a.q_off[q + 1] - a.q_off[q]);
+        if (threadIdx.x < m) {
+            const int t = a.q_terms[t0 + threadIdx.x];
+            s_term[threadIdx.x] = t;
+            s_slot[threadIdx.x] = a.dense_slot[t];
+            s_base[threadIdx.x] = a.indptr[t];
+            s_row[threadIdx.x] = a.tab.row[t];
         }
-    }
-    __syncthreads();
-    const uint32_t ne = a.ne_mask[q];
-    const unsigned long long thr = a.thr[q];
-    const uint32_t thr_score = (uint32_t)(thr >> 33);
-    const float thr_val = __uint_as_float(thr_score);
-    const long long ebase = s_base[pos];
-    const long long df = a.indptr[s_term[pos] + 1] - ebase;
-    unsigned int *ccnt = a.cand_cnt + q;
-    unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float r = 0.f;
+            s_rest[m] = 0.f;
+            for (int i = m - 1; i >= 0; i--) {
+                if (i != pos) r = __fadd_rn(r, a.gmax[s_term[i]]);
+                s_rest[i] = r;
+            }
+        }
+        __syncthreads();
+        const uint32_t ne = a.ne_mask[q];
+        const unsigned long long thr = a.thr[q];
+        const uint32_t thr_score = (uint32_t)(thr >> 33);
+        const float thr_val = __uint_as_float(thr_score);
+        const long long ebase = s_base[pos];
+        const long long df = a.indptr[s_term[pos] + 1] - ebase;
+        unsigned int *ccnt = a.cand_cnt + q;
+        unsigned long long *crow = a.cand_key + (size_t)q * (size_t)a.cap;
 #pragma unroll 1
-    for (int u = 0; u < kCandChunk / 256; u++) {
-        const long long j = (long long)chunk * kCandChunk + u * 256 + threadIdx.x;
-        if (j >= df) break;
-        const uint32_t d = (uint32_t)ld_nc_s32(a.indices + ebase + j);
-        const float ve = ld_nc_f32(a.data + ebase + j);
-        // MaxScore bound: own value + the other terms' global maxima (1e-5 relative margin
-        // for the summation order); tightened term by term as actual values replace maxima
-        if (__fmul_rn(__fadd_rn(ve, s_rest[0]), 1.00001f) < thr_val) continue;
-        float acc = 0.f;
-        bool dup = false;
-        for (int i = 0; i < m; i++) {
-            if (i == pos) {
-                acc = __fadd_rn(acc, ve);
-                continue;
-            }
-            {
-                const float rest = i < pos ? __fadd_rn(s_rest[i], ve) : s_rest[i];
-                if (__fmul_rn(__fadd_rn(acc, rest), 1.00001f) < thr_val) {
-                    dup = true;  // cannot reach the threshold any more
-                    break;
+        for (int u = 0; u < kCandChunk / 256; u++) {
+            const long long j = (long long)chunk * kCandChunk + u * 256 + threadIdx.x;
+            if (j >= df) break;
+            const uint32_t d = (uint32_t)ld_nc_s32(a.indices + ebase + j);
+            const float ve = ld_nc_f32(a.data + ebase + j);
+            // MaxScore bound: own value + the other terms' global maxima (1e-5 relative margin
+            // for the summation order); tightened term by term as actual values replace maxima
+            if (__fmul_rn(__fadd_rn(ve, s_rest[0]), 1.00001f) < thr_val) continue;
+            float acc = 0.f;
+            bool dup = false;
+            for (int i = 0; i < m; i++) {
+                if (i == pos) {
+                    acc = __fadd_rn(acc, ve);
+                    continue;
                 }
-            }
-            float val = 0.f;
-            bool present = false;
-            const int slot = s_slot[i];
-            if (slot >= 0) {
-                val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + d];
-                present = __float_as_uint(val) != 0x80000000u;
-            } else {
-                const uint2 ent = tab_lookup(a.tab, s_row[i], (int)(d >> 10));
-                const int len = (int)(ent.y & kBlkLenMask);
-                if (len) {
-                    long long lo = s_base[i] + (long long)ent.x;
-                    const long long end = lo + len;
-                    long long hi = end;
-                    while (lo < hi) {
-                        const long long mid = (lo + hi) >> 1;
-                        if ((uint32_t)a.indices[mid] < d) lo = mid + 1;
-                        else hi = mid;
-                    }
-                    if (lo < end && (uint32_t)a.indices[lo] == d) {
-                        present = true;
-                        val = a.data[lo];
+                {
+                    const float rest = i < pos ? __fadd_rn(s_rest[i], ve) : s_rest[i];
+                    if (__fmul_rn(__fadd_rn(acc, rest), 1.00001f) < thr_val) {
+                        dup = true;  // cannot reach the threshold any more
+                        break;
                     }
                 }
-            }
-            if (present) {
-                if (i < pos && !((ne >> i) & 1u)) {  // an earlier essential term owns this document
-                    dup = true;
-                    break;
+                float val = 0.f;
+                bool present = false;
+                const int slot = s_slot[i];
+                if (slot >= 0) {
+                    val = a.dense_vals[(size_t)slot * (size_t)a.dense_stride + d];
+                    present = __float_as_uint(val) != 0x80000000u;
+                } else {
+                    const uint2 ent = tab_lookup(a.tab, s_row[i], (int)(d >> 10));
+                    const int len = (int)(ent.y & kBlkLenMask);
+                    if (len) {
+                        long long lo = s_base[i] + (long long)ent.x;
+                        const long long end = lo + len;
+                        long long hi = end;
+                        while (lo < hi) {
+                            const long long mid = (lo + hi) >> 1;
+                            if ((uint32_t)a.indices[mid] < d) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo < end && (uint32_t)a.indices[lo] == d) {
+                            present = true;
+                            val = a.data[lo];
+                        }
+                    }
                 }
-                acc = __fadd_rn(acc, val);
+                if (present) {
+                    if (i < pos && !((ne >> i) & 1u)) {  // an earlier essential term owns this document
+                        dup = true;
+                        break;
+                    }
+                    acc = __fadd_rn(acc, val);
+                }
             }
+            if (!dup) emit_if_candidate(acc, d, thr_score, thr, ccnt, crow, a.cap);
         }
-        if (!dup) emit_if_candidate(acc, d, thr_score, thr, ccnt, crow, a.cap);
     }
 }
 
@@ -1611,6 +1645,75 @@ __global__ void stage_query_kernel(const InlineQuery iq, int32_t *d_src, int64_t
         d_qoff[1] = iq.n;
     }
 }
+// the same for a query that already sits on the device (sanitised workspace copy of a batch)
+__global__ void stage_query_dev_kernel(const int32_t *__restrict__ src, int n, int32_t *d_src, int64_t *d_qoff) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d_src[i] = src[i];
+    if (threadIdx.x == 0) {
+        d_qoff[0] = 0;
+        d_qoff[1] = n;
+    }
+}
+
+// workspace plan of the dense single-query passes
+struct DenseWs {
+    int32_t *d_terms;
+    uint8_t *d_nc;
+    int64_t *d_qoff, *d_qo;
+    int32_t *d_src;
+    unsigned long long *d_ctr;
+    int *d_err;
+};
+static int dense_workspace(bb25_index *idx, int n_terms, size_t extra, DenseWs &w, unsigned char **extra_ptr) {
+    const size_t nt = (size_t)(n_terms > 0 ? n_terms : 1);
+    const size_t o_terms = 0;
+    const size_t o_nc = align_up(o_terms + sizeof(int32_t) * nt);
+    const size_t o_qoff = align_up(o_nc + nt);
+    const size_t o_qo = align_up(o_qoff + 2 * sizeof(int64_t));
+    const size_t o_src = align_up(o_qo + 2 * sizeof(int64_t));
+    const size_t o_ctr = align_up(o_src + sizeof(int32_t) * nt);
+    const size_t o_err = align_up(o_ctr + sizeof(unsigned long long));
+    const size_t o_extra = align_up(o_err + sizeof(int));
+    if (ensure_workspace(idx, o_extra + extra)) return 1;
+    unsigned char *ws = (unsigned char *)idx->ws;
+    w.d_terms = (int32_t *)(ws + o_terms);
+    w.d_nc = ws + o_nc;
+    w.d_qoff = (int64_t *)(ws + o_qoff);
+    w.d_qo = (int64_t *)(ws + o_qo);
+    w.d_src = (int32_t *)(ws + o_src);
+    w.d_ctr = (unsigned long long *)(ws + o_ctr);
+    w.d_err = (int *)(ws + o_err);
+    if (extra_ptr) *extra_ptr = ws + o_extra;
+    return 0;
+}
+
+// the traversal pass of a dense single-query output; the query's terms are staged at w.d_src
+static int run_dense_staged(bb25_index *idx, int mode, const bb25_params *params, const DenseWs &w, int n_terms,
+                            float *out_scores, double *out_probs, int64_t out_stride, cudaStream_t st,
+                            const FuseSpec *fuse) {
+    BB25_CUDA(cudaMemsetAsync(w.d_err, 0, sizeof(int), st));
+    prep_queries_kernel<<<1, 32, 0, st>>>(w.d_src, w.d_qoff, 1, 0, n_terms, idx->n_vocab, nullptr, w.d_terms, w.d_nc, w.d_qo,
+                                          nullptr, nullptr, nullptr, w.d_err);
+    BB25_LAUNCH_CHECK();
+    TileArgs a{};
+    base_args(idx, a);
+    a.q_terms = w.d_terms;
+    a.q_nocount = w.d_nc;
+    a.q_off = w.d_qo;
+    a.term_base = 0;
+    a.q_list = nullptr;
+    a.n_q = 1;
+    a.tile_begin = 0;
+    a.tile_end = idx->n_tiles;
+    a.out_scores = out_scores;
+    a.out_probs = out_probs;
+    a.out_stride = out_stride;
+    if (params) a.params = *params;
+    a.work_counter = w.d_ctr;
+    if (fuse) a.fuse = *fuse;
+    if (mode == MODE_SCORES) return launch_tile<MODE_SCORES>(idx, a, st);
+    if (mode == MODE_FUSED) return launch_tile<MODE_FUSED>(idx, a, st);
+    return launch_tile<MODE_PROBS>(idx, a, st);
+}
 
 static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const int32_t *q_terms_host,
                      int n_terms, float *out_scores, double *out_probs, int64_t out_stride,
@@ -1639,54 +1742,24 @@ static int run_dense(bb25_index *idx, int mode, const bb25_params *params, const
         }
         return 0;
     }
-    const size_t o_terms = 0;
-    const size_t o_nc = align_up(o_terms + sizeof(int32_t) * (size_t)n_terms);
-    const size_t o_qoff = align_up(o_nc + (size_t)n_terms);
-    const size_t o_src = align_up(o_qoff + 2 * sizeof(int64_t));
-    const size_t o_ctr = align_up(o_src + sizeof(int32_t) * (size_t)n_terms);
-    const size_t o_err = align_up(o_ctr + sizeof(unsigned long long));
-    const size_t total = align_up(o_err + sizeof(int));
-    if (ensure_workspace(idx, total)) return 1;
-    unsigned char *ws = (unsigned char *)idx->ws;
-    int32_t *d_terms = (int32_t *)(ws + o_terms);
-    uint8_t *d_nc = ws + o_nc;
-    int64_t *d_qoff = (int64_t *)(ws + o_qoff);
-    int32_t *d_src = (int32_t *)(ws + o_src);
-    int *d_err = (int *)(ws + o_err);
+    DenseWs w;
+    ws_acquire(idx, st);
+    if (dense_workspace(idx, n_terms, 0, w, nullptr)) return 1;
     if (n_terms <= 64) {
         InlineQuery iq;
         iq.n = n_terms;
         for (int i = 0; i < n_terms; i++) iq.t[i] = q_terms_host[i];
-        stage_query_kernel<<<1, 64, 0, st>>>(iq, d_src, d_qoff);
+        stage_query_kernel<<<1, 64, 0, st>>>(iq, w.d_src, w.d_qoff);
         BB25_LAUNCH_CHECK();
     } else {
         int64_t hq[2] = {0, n_terms};
-        BB25_CUDA(cudaMemcpyAsync(d_src, q_terms_host, sizeof(int32_t) * (size_t)n_terms, cudaMemcpyHostToDevice, st));
-        BB25_CUDA(cudaMemcpyAsync(d_qoff, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
+        BB25_CUDA(cudaMemcpyAsync(w.d_src, q_terms_host, sizeof(int32_t) * (size_t)n_terms, cudaMemcpyHostToDevice, st));
+        BB25_CUDA(cudaMemcpyAsync(w.d_qoff, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
         BB25_CUDA(cudaStreamSynchronize(st));  // hq / q_terms_host are pageable stack/user memory
     }
-    BB25_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-    prep_queries_kernel<<<1, 32, 0, st>>>(d_src, d_qoff, 1, 0, idx->n_vocab, nullptr, d_terms, d_nc, nullptr, nullptr, nullptr, d_err);
-    BB25_LAUNCH_CHECK();
-    TileArgs a{};
-    base_args(idx, a);
-    a.q_terms = d_terms;
-    a.q_nocount = d_nc;
-    a.q_off = d_qoff;
-    a.term_base = 0;
-    a.q_list = nullptr;
-    a.n_q = 1;
-    a.tile_begin = 0;
-    a.tile_end = idx->n_tiles;
-    a.out_scores = out_scores;
-    a.out_probs = out_probs;
-    a.out_stride = out_stride;
-    if (params) a.params = *params;
-    a.work_counter = (unsigned long long *)(ws + o_ctr);
-    if (fuse) a.fuse = *fuse;
-    if (mode == MODE_SCORES) return launch_tile<MODE_SCORES>(idx, a, st);
-    if (mode == MODE_FUSED) return launch_tile<MODE_FUSED>(idx, a, st);
-    return launch_tile<MODE_PROBS>(idx, a, st);
+    const int rc = run_dense_staged(idx, mode, params, w, n_terms, out_scores, out_probs, out_stride, st, fuse);
+    ws_release(idx, st);
+    return rc;
 }
 
 static int check_params(const bb25_params *p) {
@@ -1699,25 +1772,145 @@ static int check_params(const bb25_params *p) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// Guaranteed path for one query: dense fp32 scores of every document, exact top-k of the
+// whole vector by (score desc, doc id asc), probabilities of the k winners from the dense
+// posterior pass.  O(N) per query, no candidate rows, no thresholds -- used for queries whose
+// threshold refinement does not settle (adversarial tie structures) and for k beyond the
+// candidate kernel's limit.
+// ---------------------------------------------------------------------------------
+__global__ void widen_scores_kernel(const float *__restrict__ s, int64_t n, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)s[i];  // exact: ranking by the fp64 value is ranking by the fp32 score
+}
+__global__ void gather_dense_row_kernel(const int64_t *__restrict__ ids, const double *__restrict__ vals,
+                                        const double *__restrict__ probs, int k, int64_t doc_id_offset,
+                                        int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                                        double *__restrict__ out_probs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= k) return;
+    const int64_t d = ids[r];
+    out_ids[r] = d + doc_id_offset;
+    if (out_scores) out_scores[r] = (float)vals[r];
+    out_probs[r] = probs[d];
+}
+
+constexpr int kMaxDenseK = 8192;
+
+// caller holds idx->mu and the device guard; the query's terms are staged in w.d_src already
+static int dense_topk_staged(bb25_index *idx, const bb25_params *params, const DenseWs &w, unsigned char *scratch,
+                             int n_terms, int k, int64_t *out_ids, float *out_scores, double *out_probs,
+                             cudaStream_t st) {
+    const size_t n = (size_t)idx->n_docs;
+    float *d_sc = (float *)scratch;
+    double *d_wide = (double *)(scratch + align_up(n * 4));
+    double *d_pr = (double *)(scratch + align_up(n * 4) + align_up(n * 8));
+    int64_t *d_ids = (int64_t *)(scratch + align_up(n * 4) + 2 * align_up(n * 8));
+    double *d_vals = (double *)(scratch + align_up(n * 4) + 2 * align_up(n * 8) + align_up((size_t)k * 8));
+    if (n_terms == 0) {
+        BB25_CUDA(cudaMemsetAsync(d_wide, 0, n * 8, st));
+        BB25_CUDA(cudaMemsetAsync(d_pr, 0, n * 8, st));
+    } else {
+        if (run_dense_staged(idx, MODE_SCORES, nullptr, w, n_terms, d_sc, nullptr, 1, st, nullptr)) return 1;
+        widen_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_sc, (int64_t)n, d_wide);
+        BB25_LAUNCH_CHECK();
+        if (run_dense_staged(idx, MODE_PROBS, params, w, n_terms, nullptr, d_pr, 1, st, nullptr)) return 1;
+    }
+    if (bb25_topk_f64(idx->device, d_wide, (int64_t)n, k, d_ids, d_vals, st)) return 1;
+    gather_dense_row_kernel<<<(k + 255) / 256, 256, 0, st>>>(d_ids, d_vals, d_pr, k, idx->doc_id_offset, out_ids, out_scores,
+                                                             out_probs);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+static size_t dense_topk_scratch_bytes(const bb25_index *idx, int k) {
+    const size_t n = (size_t)idx->n_docs;
+    return align_up(n * 4) + 2 * align_up(n * 8) + 2 * align_up((size_t)k * 8);
+}
+
+// ---------------------------------------------------------------------------------
+// small device-side bookkeeping of the batch pipeline
+// ---------------------------------------------------------------------------------
+// queries still overflowing after the last repair round of a stage are set aside
+__global__ void mark_bad_kernel(const int32_t *__restrict__ list, const unsigned int *__restrict__ n_list,
+                                uint8_t *__restrict__ bad) {
+    const unsigned int n = *n_list;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bad[list[i]] = 1;
+}
+__global__ void compact_bad_kernel(const uint8_t *__restrict__ bad, int64_t n_q, int32_t *__restrict__ list,
+                                   unsigned int *__restrict__ n_list, unsigned int *__restrict__ cand_cnt,
+                                   unsigned int *__restrict__ n_prev) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_q || !bad[q]) return;
+    list[atomicAdd(n_list, 1u)] = (int32_t)q;
+    cand_cnt[q] = 0;  // everything collected so far is collected again by the repair traversal
+    n_prev[q] = 0;
+}
+
+// what the host reads back, once, at the end of a batch
+struct BatchReport {
+    unsigned long long n_cand, units, units_skipped, units_maxscore;
+    unsigned int route[4];  // queries on the candidate path, on the block path, candidate work items (first round), -
+    unsigned int n_bad;
+    int err;
+    unsigned int reruns;
+    unsigned int pad;
+};
+__global__ void report_kernel(const unsigned long long *__restrict__ n_cand, const unsigned long long *__restrict__ stats,
+                              const unsigned int *__restrict__ route, const unsigned int *__restrict__ n_bad,
+                              const int *__restrict__ err, const unsigned int *__restrict__ round_cnt, int n_round_cnt,
+                              BatchReport *out) {
+    BatchReport r;
+    r.n_cand = *n_cand;
+    r.units = stats[0];
+    r.units_skipped = stats[1];
+    r.units_maxscore = stats[2];
+    r.route[0] = route[0];
+    r.route[1] = route[1];
+    r.route[2] = route[3];  // first-round work items (route[2] is reused by the repair rounds)
+    r.route[3] = 0;
+    r.n_bad = *n_bad;
+    r.err = *err;
+    unsigned int re = 0;
+    for (int i = 0; i < n_round_cnt; i++) re += round_cnt[i];
+    r.reruns = re;
+    r.pad = 0;
+    *out = r;
+}
+__global__ void copy_u32_kernel(const unsigned int *src, unsigned int *dst) { *dst = *src; }
+
+constexpr int kMaxRepairRounds = 6;
+
 static int retrieve_device(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
                            const int64_t *q_off, int64_t n_q, int64_t term_base, int64_t n_terms_total,
                            int k, int64_t *out_ids, float *out_scores, double *out_probs,
                            cudaStream_t st) {
-    // caller holds idx->mu and the device guard
+    // caller holds idx->mu and the device guard.  The whole batch is enqueued without a host
+    // round trip: list lengths and overflow counts stay on the device, every stage is followed by
+    // a fixed number of repair rounds (kernels that find an empty list leave at once), and ONE
+    // synchronisation at the end reads the report.
     int cap = 1024;
     while (cap < 8 * k && cap < 16384) cap <<= 1;
+    int n_rounds = 3;  // repair rounds enqueued after every stage
+    if (const char *e = getenv("BB25_REPAIR_ROUNDS")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= kMaxRepairRounds) n_rounds = v;
+    }
     const size_t nt = (size_t)(n_terms_total > 0 ? n_terms_total : 1);
     const size_t o_terms = 0;
     const size_t o_nc = align_up(o_terms + sizeof(int32_t) * nt);
-    const size_t o_thr = align_up(o_nc + nt);
+    const size_t o_qo = align_up(o_nc + nt);
+    const size_t o_thr = align_up(o_qo + sizeof(int64_t) * (size_t)(n_q + 1));
     const size_t o_cnt = align_up(o_thr + sizeof(unsigned long long) * (size_t)n_q);
     const size_t o_prev = align_up(o_cnt + sizeof(unsigned int) * (size_t)n_q);
     const size_t o_la = align_up(o_prev + sizeof(unsigned int) * (size_t)n_q);
     const size_t o_lb = align_up(o_la + sizeof(int32_t) * (size_t)n_q);
     const size_t o_ctr = align_up(o_lb + sizeof(int32_t) * (size_t)n_q);
-    const size_t o_ne = align_up(o_ctr + 128);
+    const size_t kCtrBytes = 1024;
+    const size_t o_ne = align_up(o_ctr + kCtrBytes);
     const size_t o_lista = align_up(o_ne + sizeof(uint32_t) * (size_t)n_q);
     const size_t o_listb = align_up(o_lista + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_bad = align_up(o_listb + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_badlist = align_up(o_bad + (size_t)n_q);
     // candidate-path work items: <= route_max / chunk + 24 per query
     int route_div = 32;
     if (const char *e = getenv("BB25_ROUTE_DIV")) {
@@ -1727,7 +1920,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     const long long route_max = (long long)idx->n_docs / route_div;
     const bool use_cand = use_block_kernel() && idx->prune >= 3 && idx->dense_slot != nullptr && n_q > 0;
     const size_t items_cap = use_cand ? (size_t)n_q * (size_t)(route_max / kCandChunk + 25) : 1;
-    const size_t o_info = align_up(o_listb + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_info = align_up(o_badlist + sizeof(int32_t) * (size_t)n_q);
     const size_t o_items = align_up(o_info + 2 * sizeof(longlong2) * nt);
     const size_t o_key = align_up(o_items + sizeof(uint2) * items_cap);
     const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
@@ -1735,30 +1928,40 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     unsigned char *ws = (unsigned char *)idx->ws;
     int32_t *d_terms = (int32_t *)(ws + o_terms);
     uint8_t *d_nc = ws + o_nc;
+    int64_t *d_qo = (int64_t *)(ws + o_qo);
     unsigned long long *d_thr = (unsigned long long *)(ws + o_thr);
     unsigned int *d_cnt = (unsigned int *)(ws + o_cnt);
     unsigned int *d_prev = (unsigned int *)(ws + o_prev);
     int32_t *d_list[2] = {(int32_t *)(ws + o_la), (int32_t *)(ws + o_lb)};
+    // counter block (zeroed once per batch)
     unsigned long long *d_work = (unsigned long long *)(ws + o_ctr);
-    unsigned int *d_nover = (unsigned int *)(ws + o_ctr + 8);
     int *d_err = (int *)(ws + o_ctr + 16);
     unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
     unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [3]
-    unsigned int *d_route = (unsigned int *)(ws + o_ctr + 64);  // [0] n_a, [1] n_b, [2] n_items
+    unsigned int *d_route = (unsigned int *)(ws + o_ctr + 64);  // [0] n_a, [1] n_b, [2] n_items, [3] n_items of the first round
+    unsigned int *d_nbad = (unsigned int *)(ws + o_ctr + 80);
+    unsigned int *d_round = (unsigned int *)(ws + o_ctr + 128);  // overflow counts: [stage][round], stage 0 = candidate path
+    const int kRoundStride = kMaxRepairRounds + 2;
+    BatchReport *d_report = (BatchReport *)(ws + o_ctr + 512);
+    uint8_t *d_bad = ws + o_bad;
+    int32_t *d_badlist = (int32_t *)(ws + o_badlist);
     unsigned long long *d_keys = (unsigned long long *)(ws + o_key);
 
     const float *kth = nullptr;
     if (get_kth_values(idx, k, st, &kth)) return 1;
     idx->st_launches = idx->st_passes = idx->st_reruns = idx->st_candidates = 0;
+    idx->st_syncs = 0;
     idx->ev_used = 0;
     idx->st_traverse_ms = 0.0;
     idx->st_traverse_launches = 0;
     int64_t launches0 = (int64_t)bb25_launch_count();
 
-    BB25_CUDA(cudaMemsetAsync(ws + o_ctr, 0, 128, st));
-    prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(q_terms, q_off, n_q, term_base, idx->n_vocab, kth,
-                                                                      d_terms, d_nc, d_thr, d_cnt, d_prev, d_err,
-                                                                      idx->indptr, idx->dense_vals ? idx->dense_slot : nullptr,
+    BB25_CUDA(cudaMemsetAsync(ws + o_ctr, 0, kCtrBytes, st));
+    BB25_CUDA(cudaMemsetAsync(d_bad, 0, (size_t)n_q, st));
+    prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(q_terms, q_off, n_q, term_base, (int64_t)n_terms_total,
+                                                                      idx->n_vocab, kth, d_terms, d_nc, d_qo, d_thr, d_cnt,
+                                                                      d_prev, d_err, idx->indptr,
+                                                                      idx->dense_vals ? idx->dense_slot : nullptr,
                                                                       idx->tab_row, (longlong2 *)(ws + o_info));
     BB25_LAUNCH_CHECK();
 
@@ -1789,8 +1992,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     base_args(idx, ta);
     ta.q_terms = d_terms;
     ta.q_nocount = d_nc;
-    ta.q_off = q_off;
-    ta.term_base = term_base;
+    ta.q_off = d_qo;
+    ta.term_base = 0;
     ta.thr = d_thr;
     ta.cand_cnt = d_cnt;
     ta.cand_key = d_keys;
@@ -1806,8 +2009,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.n_vocab = idx->n_vocab;
     ba.q_terms = d_terms;
     ba.qt_info = (const longlong2 *)(ws + o_info);
-    ba.q_off = q_off;
-    ba.term_base = term_base;
+    ba.q_off = d_qo;
+    ba.term_base = 0;
     ba.thr = d_thr;
     ba.cand_cnt = d_cnt;
     ba.cand_key = d_keys;
@@ -1830,7 +2033,6 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.thr = d_thr;
     sa.cap = cap;
     sa.k = k;
-    sa.n_over = d_nover;
     sa.doc_len = idx->doc_len;
     sa.avgdl = idx->avgdl;
     sa.n_docs = idx->n_docs;
@@ -1852,8 +2054,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.dense_stride = idx->dense_stride;
     sa.q_terms = d_terms;
     sa.q_nocount = d_nc;
-    sa.q_off = q_off;
-    sa.term_base = term_base;
+    sa.q_off = d_qo;
+    sa.term_base = 0;
 
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
@@ -1862,22 +2064,41 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.sort_cap = kpad;
     const size_t sel_smem = (size_t)cap * 10 + (size_t)kpad * 9 + 260 * 4;  // keys, top, hist+st, flag, rescore list
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    unsigned int *h_flags = (unsigned int *)idx->pinned;  // [0] n_over, [1] err
+    // grid of a select launch whose list length is only known on the device (repair rounds)
+    const unsigned repair_grid = (unsigned)std::min<int64_t>(n_q, (int64_t)idx->sm_count * 2);
+
+    auto timed_begin = [&]() -> int {
+        const int pair = idx->ev_used < bb25_index::kMaxEv ? idx->ev_used : -1;
+        if (pair >= 0) {
+            while (idx->n_ev < 2 * (pair + 1)) {
+                if (cudaEventCreate(&idx->ev[idx->n_ev]) != cudaSuccess) return -1;
+                idx->n_ev++;
+            }
+            cudaEventRecord(idx->ev[2 * pair], st);
+        }
+        return pair;
+    };
+    auto timed_end = [&](int pair) {
+        if (pair >= 0) {
+            cudaEventRecord(idx->ev[2 * pair + 1], st);
+            idx->ev_used++;
+        }
+    };
 
     idx->st_routed = 0;
     idx->st_cand_items = 0;
-    int64_t units_host = 0;  // (block, query) units handed to block_kernel
 
     // ---- candidate-driven queries (pruning level 3) ---------------------------------
-    const int32_t *blk_list = nullptr;  // queries left to the block traversal (nullptr = all)
-    int blk_n = (int)n_q;
+    const int32_t *blk_list = nullptr;        // queries left to the block traversal (nullptr = all)
+    const unsigned int *blk_n_ptr = nullptr;  // their number, on the device
+    RouteArgs ra{};
+    CandArgs ca{};
     if (use_cand) {
         const float *gmax = nullptr;
         if (get_kth_values(idx, 1, st, &gmax)) return 1;
-        RouteArgs ra{};
         ra.q_terms = d_terms;
-        ra.q_off = q_off;
-        ra.term_base = term_base;
+        ra.q_off = d_qo;
+        ra.term_base = 0;
         ra.n_q = n_q;
         ra.thr = d_thr;
         ra.gmax = gmax;
@@ -1893,20 +2114,10 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         ra.items_cap = (unsigned int)std::min<size_t>(items_cap, 0xFFFFFFF0u);
         route_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(ra);
         BB25_LAUNCH_CHECK();
-        unsigned int *h_r = (unsigned int *)idx->pinned + 8;
-        BB25_CUDA(cudaMemcpyAsync(h_r, d_route, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        BB25_CUDA(cudaMemcpyAsync(&h_flags[1], d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-        BB25_CUDA(cudaStreamSynchronize(st));
-        if (h_flags[1]) {
-            set_error("invalid query batch (flags=%u: 1 term id out of range, 2 q_off not monotone)", h_flags[1]);
-            return 1;
-        }
-        int n_a = (int)h_r[0];
-        unsigned int n_items = h_r[2];
+        copy_u32_kernel<<<1, 1, 0, st>>>(d_route + 2, d_route + 3);
+        BB25_LAUNCH_CHECK();
         blk_list = ra.list_b;
-        blk_n = (int)h_r[1];
-        idx->st_routed = n_a;
-        CandArgs ca{};
+        blk_n_ptr = d_route + 1;
         ca.data = idx->data;
         ca.indices = idx->indices;
         ca.indptr = idx->indptr;
@@ -1916,124 +2127,197 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         ca.dense_vals = idx->dense_vals;
         ca.dense_stride = idx->dense_stride;
         ca.q_terms = d_terms;
-        ca.q_off = q_off;
-        ca.term_base = term_base;
+        ca.q_off = d_qo;
+        ca.term_base = 0;
         ca.ne_mask = ra.ne_mask;
         ca.items = ra.items;
+        ca.n_items = d_route + 2;
         ca.thr = d_thr;
         ca.cand_cnt = d_cnt;
         ca.cand_key = d_keys;
         ca.cap = cap;
         ca.gmax = gmax;
-        const int32_t *a_list = ra.list_a;
-        int flip = 0;
-        for (int iter = 0; n_a > 0; iter++) {
-            if (iter > 200) { set_error("threshold refinement did not converge"); return 1; }
-            const int pair = idx->ev_used < bb25_index::kMaxEv ? idx->ev_used : -1;
-            if (pair >= 0) {
-                while (idx->n_ev < 2 * (pair + 1)) {
-                    BB25_CUDA(cudaEventCreate(&idx->ev[idx->n_ev]));
-                    idx->n_ev++;
-                }
-                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair], st));
-            }
-            if (n_items > 0) {
-                cand_kernel<<<n_items, 256, 0, st>>>(ca);
+        const unsigned cand_grid = (unsigned)idx->sm_count * 8;
+        unsigned int *rc = d_round;  // stage 0
+        for (int r = 0; r <= n_rounds; r++) {
+            // round 0: every routed query; round r: the queries whose row overflowed in round r-1
+            const int32_t *list = r == 0 ? ra.list_a : d_list[(r - 1) & 1];
+            const unsigned int *n_list = r == 0 ? d_route : rc + r;
+            if (r > 0) {
+                BB25_CUDA(cudaMemsetAsync(ra.n_items, 0, sizeof(unsigned int), st));
+                rebuild_items_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(ra, list, n_list);
                 BB25_LAUNCH_CHECK();
             }
-            if (pair >= 0) {
-                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair + 1], st));
-                idx->ev_used++;
-            }
-            idx->st_cand_items += n_items;
+            const int pair = timed_begin();
+            cand_kernel<<<cand_grid, 256, 0, st>>>(ca);
+            BB25_LAUNCH_CHECK();
+            timed_end(pair);
             idx->st_passes++;
-            BB25_CUDA(cudaMemsetAsync(d_nover, 0, sizeof(unsigned int), st));
-            sa.q_list = a_list;
+            sa.q_list = list;
+            sa.n_list = 0;
+            sa.n_list_ptr = n_list;
             sa.final_pass = 1;
-            sa.over_list = d_list[flip];
-            select_kernel<512><<<(unsigned)n_a, 512, sel_smem, st>>>(sa);
+            sa.rescore = 0;
+            sa.over_list = d_list[r & 1];
+            sa.n_over = rc + r + 1;
+            select_kernel<512><<<r == 0 ? (unsigned)n_q : repair_grid, 512, sel_smem, st>>>(sa);
             BB25_LAUNCH_CHECK();
-            BB25_CUDA(cudaMemcpyAsync(&h_flags[0], d_nover, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            BB25_CUDA(cudaStreamSynchronize(st));
-            const unsigned int n_over = h_flags[0];
-            if (n_over == 0) break;
-            idx->st_reruns += n_over;
-            // tighter thresholds are in place; evaluate those queries' candidates again
-            a_list = d_list[flip];
-            n_a = (int)n_over;
-            flip ^= 1;
-            BB25_CUDA(cudaMemsetAsync(ra.n_items, 0, sizeof(unsigned int), st));
-            rebuild_items_kernel<<<(unsigned)((n_a + 127) / 128), 128, 0, st>>>(ra, a_list, n_a);
-            BB25_LAUNCH_CHECK();
-            BB25_CUDA(cudaMemcpyAsync(h_r, d_route, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            BB25_CUDA(cudaStreamSynchronize(st));
-            n_items = h_r[2];
         }
+        mark_bad_kernel<<<4, 256, 0, st>>>(d_list[n_rounds & 1], rc + n_rounds + 1, d_bad);
+        BB25_LAUNCH_CHECK();
     }
 
     // ---- block / tile traversal of the remaining queries, group by group -----------
-    for (int gi = 0; gi < ng && blk_n > 0; gi++) {
-        int cur_n = blk_n;
-        const int32_t *cur_list = blk_list;
-        int flip = 0;
-        for (int iter = 0;; iter++) {
-            if (iter > 200) { set_error("threshold refinement did not converge"); return 1; }
-            ta.q_list = cur_list;
-            ta.n_q = cur_n;
-            ta.tile_begin = bounds[gi];
-            ta.tile_end = bounds[gi + 1];
-            const int pair = idx->ev_used < bb25_index::kMaxEv ? idx->ev_used : -1;
-            if (pair >= 0) {
-                while (idx->n_ev < 2 * (pair + 1)) {
-                    BB25_CUDA(cudaEventCreate(&idx->ev[idx->n_ev]));
-                    idx->n_ev++;
-                }
-                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair], st));
-            }
+    for (int gi = 0; gi < ng; gi++) {
+        unsigned int *rc = d_round + (size_t)(gi + 1) * kRoundStride;
+        for (int r = 0; r <= n_rounds; r++) {
+            const int32_t *list = r == 0 ? blk_list : d_list[(r - 1) & 1];
+            const unsigned int *n_list = r == 0 ? blk_n_ptr : rc + r;
+            const bool first = r == 0;
+            const int pair = timed_begin();
             if (blockk) {
-                ba.q_list = cur_list;
-                ba.n_q = cur_n;
+                ba.q_list = list;
+                ba.n_q = (int)n_q;
+                ba.n_q_ptr = n_list;
                 ba.blk_begin = bounds[gi];
                 ba.blk_end = bounds[gi + 1];
-                if (launch_block(idx, ba, !(relaxed && iter == 0), st)) return 1;
-                units_host += (int64_t)(ba.blk_end - ba.blk_begin) * (int64_t)cur_n;
-            } else if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) {
-                return 1;
+                if (launch_block(idx, ba, !(relaxed && first), st)) return 1;
+            } else {
+                ta.q_list = list;
+                ta.n_q = (int)n_q;
+                ta.n_q_ptr = n_list;
+                ta.tile_begin = bounds[gi];
+                ta.tile_end = bounds[gi + 1];
+                if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) return 1;
             }
-            if (pair >= 0) {
-                BB25_CUDA(cudaEventRecord(idx->ev[2 * pair + 1], st));
-                idx->ev_used++;
-            }
+            timed_end(pair);
             idx->st_passes++;
-            BB25_CUDA(cudaMemsetAsync(d_nover, 0, sizeof(unsigned int), st));
-            sa.q_list = cur_list;
-            sa.rescore = (blockk && relaxed && iter == 0) ? 1 : 0;
+            sa.q_list = list;
+            sa.n_list = (int)n_q;
+            sa.n_list_ptr = n_list;
+            sa.rescore = (blockk && relaxed && first) ? 1 : 0;
             sa.final_pass = (gi == ng - 1) ? 1 : 0;
-            sa.over_list = d_list[flip];
-            select_kernel<512><<<(unsigned)cur_n, 512, sel_smem, st>>>(sa);
+            sa.over_list = d_list[r & 1];
+            sa.n_over = rc + r + 1;
+            select_kernel<512><<<first ? (unsigned)n_q : repair_grid, 512, sel_smem, st>>>(sa);
             BB25_LAUNCH_CHECK();
-            BB25_CUDA(cudaMemcpyAsync(&h_flags[0], d_nover, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            BB25_CUDA(cudaMemcpyAsync(&h_flags[1], d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-            BB25_CUDA(cudaStreamSynchronize(st));
-            if (h_flags[1]) {
-                set_error("invalid query batch (flags=%u: 1 term id out of range, 2 q_off not monotone)", h_flags[1]);
+        }
+        mark_bad_kernel<<<4, 256, 0, st>>>(d_list[n_rounds & 1], rc + n_rounds + 1, d_bad);
+        BB25_LAUNCH_CHECK();
+        if (gi + 1 < ng && idx->exchange_cb) {
+            // sharded retrieval: the ranks agree on tighter thresholds between block groups
+            if (idx->exchange_cb(idx->exchange_user, (void *)d_thr, (void *)d_cnt, (void *)d_keys, n_q, cap, k, gi, (void *)st)) {
+                set_error("threshold exchange callback failed");
                 return 1;
             }
-            const unsigned int n_over = h_flags[0];
-            if (n_over == 0) break;
-            idx->st_reruns += n_over;
-            cur_list = d_list[flip];
-            cur_n = (int)n_over;
-            flip ^= 1;
         }
     }
-    BB25_CUDA(cudaMemcpyAsync(idx->pinned, d_ncand, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    compact_bad_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, st>>>(d_bad, n_q, d_badlist, d_nbad, d_cnt, d_prev);
+    BB25_LAUNCH_CHECK();
+    report_kernel<<<1, 1, 0, st>>>(d_ncand, d_stats, d_route, d_nbad, d_err, d_round, (ng + 1) * kRoundStride, d_report);
+    BB25_LAUNCH_CHECK();
+    BatchReport *h_rep = (BatchReport *)idx->pinned;
+    BB25_CUDA(cudaMemcpyAsync(h_rep, d_report, sizeof(BatchReport), cudaMemcpyDeviceToHost, st));
     BB25_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long *h_c = (const unsigned long long *)idx->pinned;
-    idx->st_candidates = (int64_t)h_c[0];
-    idx->st_units = blockk ? units_host : (int64_t)h_c[1];
-    idx->st_units_skipped = (int64_t)h_c[2];
-    idx->st_units_maxscore = (int64_t)h_c[3];
+    idx->st_syncs++;
+    if (h_rep->err) {
+        set_error("invalid query batch (flags=%d: 1 term id out of range, 2 q_off not monotone / outside the batch)", h_rep->err);
+        return 1;
+    }
+    idx->st_candidates = (int64_t)h_rep->n_cand;
+    idx->st_units = (int64_t)h_rep->units;
+    idx->st_units_skipped = (int64_t)h_rep->units_skipped;
+    idx->st_units_maxscore = (int64_t)h_rep->units_maxscore;
+    idx->st_routed = (int64_t)h_rep->route[0];
+    idx->st_cand_items = (int64_t)h_rep->route[2];
+    idx->st_reruns = (int64_t)h_rep->reruns;
+
+    // ---- rare: queries whose rows still overflowed after the enqueued repair rounds ----------
+    // They are evaluated again over ALL blocks against their (by now tight) thresholds in query
+    // order, host-driven; whatever is left after a few such passes takes the dense guaranteed path.
+    unsigned int n_bad = h_rep->n_bad;
+    idx->st_bad = (int64_t)n_bad;
+    if (n_bad > 0) {
+        const int32_t *list = d_badlist;
+        unsigned int *d_cntr = d_round;  // counters are free again
+        unsigned int *h_n = (unsigned int *)((unsigned char *)idx->pinned + 512);
+        int flip = 0;
+        for (int iter = 0; n_bad > 0 && iter < 6; iter++) {
+            BB25_CUDA(cudaMemsetAsync(d_cntr, 0, sizeof(unsigned int), st));
+            if (blockk) {
+                ba.q_list = list;
+                ba.n_q = (int)n_bad;
+                ba.n_q_ptr = nullptr;
+                ba.blk_begin = 0;
+                ba.blk_end = T;
+                if (launch_block(idx, ba, true, st)) return 1;
+            } else {
+                ta.q_list = list;
+                ta.n_q = (int)n_bad;
+                ta.n_q_ptr = nullptr;
+                ta.tile_begin = 0;
+                ta.tile_end = T;
+                if (launch_tile<MODE_RETRIEVE>(idx, ta, st)) return 1;
+            }
+            idx->st_passes++;
+            sa.q_list = list;
+            sa.n_list = (int)n_bad;
+            sa.n_list_ptr = nullptr;
+            sa.rescore = 0;
+            sa.final_pass = 1;
+            sa.over_list = d_list[flip];
+            sa.n_over = d_cntr;
+            select_kernel<512><<<n_bad, 512, sel_smem, st>>>(sa);
+            BB25_LAUNCH_CHECK();
+            BB25_CUDA(cudaMemcpyAsync(h_n, d_cntr, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            BB25_CUDA(cudaStreamSynchronize(st));
+            idx->st_syncs++;
+            n_bad = *h_n;
+            list = d_list[flip];
+            flip ^= 1;
+        }
+        if (n_bad > 0) {
+            // dense guaranteed path, one query at a time (terms come from the sanitised device copy)
+            std::vector<int32_t> h_list(n_bad);
+            BB25_CUDA(cudaMemcpyAsync(h_list.data(), list, sizeof(int32_t) * n_bad, cudaMemcpyDeviceToHost, st));
+            std::vector<int64_t> h_qo((size_t)n_q + 1);
+            BB25_CUDA(cudaMemcpyAsync(h_qo.data(), d_qo, sizeof(int64_t) * (size_t)(n_q + 1), cudaMemcpyDeviceToHost, st));
+            BB25_CUDA(cudaStreamSynchronize(st));
+            idx->st_syncs++;
+            if (k > kMaxDenseK) { set_error("threshold refinement did not converge"); return 1; }
+            // the dense pass needs its own scratch and its own small workspace: the batch workspace
+            // (sanitised terms) must stay alive, so both come from a temporary allocation
+            unsigned char *tmp = nullptr;
+            int max_m = 1;
+            for (unsigned int i = 0; i < n_bad; i++) max_m = std::max<int>(max_m, (int)(h_qo[h_list[i] + 1] - h_qo[h_list[i]]));
+            const size_t small = align_up(sizeof(int32_t) * (size_t)max_m) * 2 + align_up((size_t)max_m) + 5 * 256;
+            BB25_CUDA(cudaMalloc(&tmp, small + dense_topk_scratch_bytes(idx, k)));
+            DenseWs w;
+            unsigned char *p = tmp;
+            w.d_terms = (int32_t *)p; p += align_up(sizeof(int32_t) * (size_t)max_m);
+            w.d_src = (int32_t *)p; p += align_up(sizeof(int32_t) * (size_t)max_m);
+            w.d_nc = p; p += align_up((size_t)max_m);
+            w.d_qoff = (int64_t *)p; p += 256;
+            w.d_qo = (int64_t *)p; p += 256;
+            w.d_ctr = (unsigned long long *)p; p += 256;
+            w.d_err = (int *)p; p += 256;
+            p += 256;
+            int rc = 0;
+            for (unsigned int i = 0; i < n_bad && !rc; i++) {
+                const int q = h_list[i];
+                const int m = (int)std::max<int64_t>(0, h_qo[q + 1] - h_qo[q]);
+                stage_query_dev_kernel<<<1, 128, 0, st>>>(d_terms + h_qo[q], m, w.d_src, w.d_qoff);
+                count_launch();
+                rc = dense_topk_staged(idx, params, w, p, m, k, out_ids + (size_t)q * k,
+                                       out_scores ? out_scores + (size_t)q * k : nullptr, out_probs + (size_t)q * k, st);
+            }
+            cudaStreamSynchronize(st);
+            idx->st_syncs++;
+            cudaFree(tmp);
+            if (rc) return 1;
+            idx->st_dense_fallback = (int64_t)n_bad;
+        }
+    }
     for (int i = 0; i < idx->ev_used; i++) {
         float ms = 0.f;
         BB25_CUDA(cudaEventElapsedTime(&ms, idx->ev[2 * i], idx->ev[2 * i + 1]));
@@ -2070,9 +2354,10 @@ int bb25_fuse_bm25_signal(bb25_index *idx, const bb25_params *params, const int3
     return run_dense(idx, MODE_FUSED, params, q_terms, n_terms, nullptr, acc, 1, (cudaStream_t)stream, &f);
 }
 
-int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
-                        const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
-                        float *out_scores, double *out_probs, void *stream) {
+static int retrieve_checked(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                            const int64_t *q_off, int64_t n_queries, int64_t term_base, int64_t n_terms_total,
+                            int k, int64_t *out_ids, float *out_scores, double *out_probs, cudaStream_t st,
+                            bool read_ends) {
     if (!idx) { set_error("index is NULL"); return 1; }
     if (check_params(params)) return 1;
     if (n_queries < 0 || !q_off || !out_ids || !out_probs) { set_error("bad arguments"); return 1; }
@@ -2085,15 +2370,38 @@ int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_
     DeviceGuard g(idx->device);
     if (!g.ok) { set_error("cannot select device"); return 1; }
     std::lock_guard<std::mutex> lock(idx->mu);
-    cudaStream_t st = (cudaStream_t)stream;
-    int64_t ends[2];
-    BB25_CUDA(cudaMemcpyAsync(&ends[0], q_off, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    BB25_CUDA(cudaMemcpyAsync(&ends[1], q_off + n_queries, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    BB25_CUDA(cudaStreamSynchronize(st));
-    if (ends[1] < ends[0] || ends[0] < 0) { set_error("bad q_off"); return 1; }
-    if (ends[1] > ends[0] && !q_terms) { set_error("q_terms is NULL"); return 1; }
-    return retrieve_device(idx, params, q_terms, q_off, n_queries, ends[0], ends[1] - ends[0], k, out_ids,
-                           out_scores, out_probs, st);
+    int extra_syncs = 0;
+    if (read_ends) {
+        int64_t ends[2];
+        BB25_CUDA(cudaMemcpyAsync(&ends[0], q_off, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        BB25_CUDA(cudaMemcpyAsync(&ends[1], q_off + n_queries, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        BB25_CUDA(cudaStreamSynchronize(st));
+        extra_syncs = 1;
+        term_base = ends[0];
+        n_terms_total = ends[1] - ends[0];
+    }
+    if (n_terms_total < 0 || term_base < 0) { set_error("bad q_off"); return 1; }
+    if (n_terms_total > 0 && !q_terms) { set_error("q_terms is NULL"); return 1; }
+    ws_acquire(idx, st);
+    const int rc = retrieve_device(idx, params, q_terms, q_off, n_queries, term_base, n_terms_total, k, out_ids,
+                                   out_scores, out_probs, st);
+    ws_release(idx, st);
+    idx->st_syncs += extra_syncs;
+    return rc;
+}
+
+int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                        const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
+                        float *out_scores, double *out_probs, void *stream) {
+    return retrieve_checked(idx, params, q_terms, q_off, n_queries, 0, 0, k, out_ids, out_scores, out_probs,
+                            (cudaStream_t)stream, true);
+}
+
+int bb25_retrieve_batch_ex(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                           const int64_t *q_off, int64_t n_queries, int64_t term_base, int64_t n_terms_total,
+                           int k, int64_t *out_ids, float *out_scores, double *out_probs, void *stream) {
+    return retrieve_checked(idx, params, q_terms, q_off, n_queries, term_base, n_terms_total, k, out_ids, out_scores,
+                            out_probs, (cudaStream_t)stream, false);
 }
 
 int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
@@ -2102,42 +2410,103 @@ int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const i
     if (!idx) { set_error("index is NULL"); return 1; }
     if (n_queries < 0 || !q_off || !out_ids || !out_probs) { set_error("bad arguments"); return 1; }
     if (n_queries == 0) return 0;
+    if (k < 1) { set_error("k must be >= 1"); return 1; }
     DeviceGuard g(idx->device);
     if (!g.ok) { set_error("cannot select device"); return 1; }
     const int64_t nt = q_off[n_queries] - q_off[0];
     if (nt < 0) { set_error("bad q_off"); return 1; }
-    const size_t nk = (size_t)n_queries * (size_t)(k > 0 ? k : 1);
-    int32_t *d_terms = nullptr;
-    int64_t *d_off = nullptr, *d_ids = nullptr;
-    float *d_sc = nullptr;
-    double *d_pr = nullptr;
-    int rc = 1;
-    cudaStream_t st = nullptr;
-    do {
-        if (cudaMalloc(&d_terms, sizeof(int32_t) * (size_t)(nt > 0 ? nt : 1)) != cudaSuccess) break;
-        if (cudaMalloc(&d_off, sizeof(int64_t) * (size_t)(n_queries + 1)) != cudaSuccess) break;
-        if (cudaMalloc(&d_ids, sizeof(int64_t) * nk) != cudaSuccess) break;
-        if (cudaMalloc(&d_sc, sizeof(float) * nk) != cudaSuccess) break;
-        if (cudaMalloc(&d_pr, sizeof(double) * nk) != cudaSuccess) break;
-        if (nt > 0 && cudaMemcpyAsync(d_terms, q_terms + q_off[0], sizeof(int32_t) * (size_t)nt, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-        if (cudaMemcpyAsync(d_off, q_off, sizeof(int64_t) * (size_t)(n_queries + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-        // d_terms holds positions [q_off[0], q_off[Q]) -> pass a base-shifted pointer
-        rc = bb25_retrieve_batch(idx, params, d_terms - q_off[0], d_off, n_queries, k, d_ids, d_sc, d_pr, st);
-        if (rc) break;
-        rc = 1;
-        if (cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * nk, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-        if (out_scores && cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * nk, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-        if (cudaMemcpyAsync(out_probs, d_pr, sizeof(double) * nk, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-        if (cudaStreamSynchronize(st) != cudaSuccess) break;
-        rc = 0;
-    } while (0);
-    if (rc && bb25_last_error()[0] == 0) set_error("CUDA failure in bb25_retrieve_batch_host: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(d_terms);
-    cudaFree(d_off);
-    cudaFree(d_ids);
-    cudaFree(d_sc);
-    cudaFree(d_pr);
+    const size_t nk = (size_t)n_queries * (size_t)k;
+    // device staging area and stream owned by the handle, grown on demand and kept (no per-call
+    // allocation); the copies are asynchronous when the caller's buffers are page-locked
+    const size_t o_terms = 0;
+    const size_t o_off = align_up(o_terms + sizeof(int32_t) * (size_t)(nt > 0 ? nt : 1));
+    const size_t o_ids = align_up(o_off + sizeof(int64_t) * (size_t)(n_queries + 1));
+    const size_t o_pr = align_up(o_ids + sizeof(int64_t) * nk);
+    const size_t o_sc = align_up(o_pr + sizeof(double) * nk);
+    const size_t total = align_up(o_sc + sizeof(float) * nk);
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        if (!idx->hs_stream) BB25_CUDA(cudaStreamCreateWithFlags(&idx->hs_stream, cudaStreamNonBlocking));
+        if (total > idx->hs_bytes) {
+            if (idx->hs_dev) {
+                BB25_CUDA(cudaStreamSynchronize(idx->hs_stream));
+                BB25_CUDA(cudaFree(idx->hs_dev));
+                idx->hs_dev = nullptr;
+                idx->hs_bytes = 0;
+            }
+            const size_t want = total + (total >> 3);
+            BB25_CUDA(cudaMalloc(&idx->hs_dev, want));
+            idx->hs_bytes = want;
+        }
+    }
+    cudaStream_t st = idx->hs_stream;
+    unsigned char *base = (unsigned char *)idx->hs_dev;
+    int32_t *d_terms = (int32_t *)(base + o_terms);
+    int64_t *d_off = (int64_t *)(base + o_off);
+    int64_t *d_ids = (int64_t *)(base + o_ids);
+    double *d_pr = (double *)(base + o_pr);
+    float *d_sc = (float *)(base + o_sc);
+    if (nt > 0) BB25_CUDA(cudaMemcpyAsync(d_terms, q_terms + q_off[0], sizeof(int32_t) * (size_t)nt, cudaMemcpyHostToDevice, st));
+    BB25_CUDA(cudaMemcpyAsync(d_off, q_off, sizeof(int64_t) * (size_t)(n_queries + 1), cudaMemcpyHostToDevice, st));
+    // d_terms holds positions [q_off[0], q_off[Q]): the batch's first term is element 0 of d_terms
+    if (retrieve_checked(idx, params, d_terms - q_off[0], d_off, n_queries, q_off[0], nt, k, d_ids, d_sc, d_pr, st, false))
+        return 1;
+    BB25_CUDA(cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * nk, cudaMemcpyDeviceToHost, st));
+    if (out_scores) BB25_CUDA(cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * nk, cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaMemcpyAsync(out_probs, d_pr, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+    BB25_CUDA(cudaStreamSynchronize(st));
+    idx->st_syncs++;
+    return 0;
+}
+
+int bb25_retrieve_one_dense(bb25_index *idx, const bb25_params *params, const int32_t *q_terms, int n_terms, int k,
+                            int64_t *out_ids, float *out_scores, double *out_probs, void *stream) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (check_params(params)) return 1;
+    if (n_terms < 0 || (n_terms > 0 && !q_terms) || !out_ids || !out_probs) { set_error("bad arguments"); return 1; }
+    if (k < 1 || k > kMaxDenseK || (int64_t)k > idx->n_docs) {
+        set_error("k must satisfy 1 <= k <= min(n_docs, %d), got %d", kMaxDenseK, k);
+        return 1;
+    }
+    for (int i = 0; i < n_terms; i++)
+        if (q_terms[i] < 0 || q_terms[i] >= idx->n_vocab) {
+            set_error("query term id %d out of range [0, %lld)", q_terms[i], (long long)idx->n_vocab);
+            return 1;
+        }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("cannot select device"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    DenseWs w;
+    unsigned char *scratch = nullptr;
+    ws_acquire(idx, st);
+    if (dense_workspace(idx, n_terms, dense_topk_scratch_bytes(idx, k), w, &scratch)) return 1;
+    if (n_terms > 0) {
+        int64_t hq[2] = {0, n_terms};
+        BB25_CUDA(cudaMemcpyAsync(w.d_src, q_terms, sizeof(int32_t) * (size_t)n_terms, cudaMemcpyHostToDevice, st));
+        BB25_CUDA(cudaMemcpyAsync(w.d_qoff, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
+        BB25_CUDA(cudaStreamSynchronize(st));
+    }
+    const int rc = dense_topk_staged(idx, params, w, scratch, n_terms, k, out_ids, out_scores, out_probs, st);
+    ws_release(idx, st);
     return rc;
+}
+
+int bb25_index_set_threshold_exchange(bb25_index *idx, bb25_exchange_fn fn, void *user) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->exchange_cb = fn;
+    idx->exchange_user = user;
+    return 0;
+}
+
+int bb25_retrieve_sync_stats(const bb25_index *idx, int64_t *host_syncs, int64_t *repaired_queries,
+                             int64_t *dense_fallback_queries) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (host_syncs) *host_syncs = idx->st_syncs;
+    if (repaired_queries) *repaired_queries = idx->st_bad;
+    if (dense_fallback_queries) *dense_fallback_queries = idx->st_dense_fallback;
+    return 0;
 }
 
 int bb25_retrieve_stats(const bb25_index *idx, int64_t *launches, int64_t *passes, int64_t *rerun_queries,

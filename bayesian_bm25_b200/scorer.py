@@ -10,7 +10,9 @@ libbb25 (include/bb25.h).  Extensions for corpora that do not fit Python lists:
 from __future__ import annotations
 
 import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
+from itertools import chain, repeat
 
 import numpy as np
 import torch
@@ -20,7 +22,10 @@ from .probability import BayesianProbabilityTransform
 
 _VALID_BASE_RATE_METHODS = estimators.VALID_BASE_RATE_METHODS
 MAX_DEVICE_K = 4096      # bb25_retrieve_batch limit; larger k takes the dense path
+MAX_DENSE_K = 8192       # bb25_retrieve_one_dense limit
 QUERY_CHUNK = 16384      # queries per bb25_retrieve_batch call (bounds the workspace)
+PIPELINE_CHUNKS = 4      # retrieve(list[list[str]]): chunks whose token->id mapping overlaps the device work
+PIPELINE_MIN_CHUNK = 1024
 
 
 class BlockMaxIndex:
@@ -234,6 +239,11 @@ class BayesianBM25Scorer:
             base_rate = float(self._user_base_rate)
         self._transform = BayesianProbabilityTransform(alpha=alpha, beta=beta, base_rate=base_rate)
 
+    def set_vocabulary(self, tokens) -> None:
+        """Extension: token strings of a prebuilt CSC's term ids (tokens[i] is term i), so that the
+        string-level retrieve()/get_probabilities() work on an index adopted with index_from_csc()."""
+        self._vocab = {t: i for i, t in enumerate(tokens)}
+
     @staticmethod
     def _pseudo_query_docs(n: int) -> np.ndarray:
         """Documents whose first five tokens serve as pseudo-queries (scorer.py:295-298)."""
@@ -250,8 +260,30 @@ class BayesianBM25Scorer:
         v = self._vocab
         return np.asarray([v[t] for t in tokens if t in v], dtype=np.int32)
 
+    def _term_ids_batch(self, query_tokens):
+        """Token lists -> (flat in-vocabulary ids int32, offsets int64[Q+1]); out-of-vocabulary
+        tokens are dropped, order and duplicates kept (what bm25s does with a query)."""
+        nq = len(query_tokens)
+        lens = np.fromiter(map(len, query_tokens), dtype=np.int64, count=nq)
+        total = int(lens.sum())
+        ids = np.fromiter(map(self._vocab.get, chain.from_iterable(query_tokens), repeat(-1)), dtype=np.int64,
+                          count=total)
+        keep = ids >= 0
+        off = np.zeros(nq + 1, dtype=np.int64)
+        if total:
+            ends = np.cumsum(lens)
+            kept = np.concatenate(([0], np.cumsum(keep)))
+            off[1:] = kept[ends]
+        return ids[keep].astype(np.int32), off
+
     def _params(self) -> _lib.Params:
         t = self._transform
+        if t._prior_fn is not None and t._training_mode != "prior_free":
+            # probability.py:194-199 evaluates a Python callback per document; the fused kernels
+            # cannot, and silently ignoring it would change the numbers
+            raise NotImplementedError(
+                "the transform has a custom prior_fn: the fused retrieve/get_probabilities kernels evaluate the "
+                "composite prior only; use get_scores_ids() + transform.score_to_probability() for a custom prior")
         return _lib.make_params(t.alpha, t.beta, t.base_rate, prior_free=t._training_mode == "prior_free")
 
     def _scores_device(self, term_ids: np.ndarray) -> torch.Tensor:
@@ -300,9 +332,11 @@ class BayesianBM25Scorer:
             raise RuntimeError("Call index() before get_probabilities().")
         return self.probabilities_device(self._term_ids(query_tokens)).cpu().numpy()
 
-    def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
+    def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int, host_off=None):
         """Device-resident batch retrieve: q_terms int32 [total], q_off int64 [Q+1]
-        CUDA tensors -> (ids int64 [Q,k], scores fp32 [Q,k], probs fp64 [Q,k]) CUDA tensors."""
+        CUDA tensors -> (ids int64 [Q,k], scores fp32 [Q,k], probs fp64 [Q,k]) CUDA tensors.
+        `host_off` (the same offsets on the host) lets the library enqueue the whole batch
+        without reading anything back first."""
         self._require_index("retrieve()")
         nq = q_off.numel() - 1
         ids = torch.empty((nq, k), dtype=torch.int64, device=self._device)
@@ -311,48 +345,78 @@ class BayesianBM25Scorer:
         p = self._params()
         for s in range(0, nq, QUERY_CHUNK):
             e = min(nq, s + QUERY_CHUNK)
-            _lib.check(_lib.lib().bb25_retrieve_batch(
-                self._handle, C.byref(p), q_terms.data_ptr(), q_off[s:].data_ptr(), e - s, k,
-                ids[s:].data_ptr(), sc[s:].data_ptr(), pr[s:].data_ptr(), _lib.stream_ptr()))
+            if host_off is not None:
+                _lib.check(_lib.lib().bb25_retrieve_batch_ex(
+                    self._handle, C.byref(p), q_terms.data_ptr(), q_off[s:].data_ptr(), e - s, int(host_off[s]),
+                    int(host_off[e] - host_off[s]), k, ids[s:].data_ptr(), sc[s:].data_ptr(), pr[s:].data_ptr(),
+                    _lib.stream_ptr()))
+            else:
+                _lib.check(_lib.lib().bb25_retrieve_batch(
+                    self._handle, C.byref(p), q_terms.data_ptr(), q_off[s:].data_ptr(), e - s, k,
+                    ids[s:].data_ptr(), sc[s:].data_ptr(), pr[s:].data_ptr(), _lib.stream_ptr()))
         return ids, sc, pr
 
     def retrieve_ids(self, q_terms, q_off, k: int = 10, return_scores: bool = False):
         """Extension: batch retrieve for queries given as in-vocabulary term ids
-        (flat int32 array + int64 offsets), host in / host out."""
+        (flat int32 array + int64 offsets), host in / host out, through the C ABI's
+        host-buffer entry point (bb25_retrieve_batch_host) with page-locked buffers."""
         self._require_index("retrieve()")
         if k > self._num_docs:
             raise ValueError(
                 f"k of {k} is larger than the number of available scores, which is {self._num_docs}")
         q_terms = np.ascontiguousarray(q_terms, dtype=np.int32)
         q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        nq = q_off.size - 1
         if k > MAX_DEVICE_K:
             return self._retrieve_large_k(q_terms, q_off, k, return_scores)
-        # inputs go up from pinned staging, results come back into pinned buffers
-        # (torch's caching host allocator recycles them), one sync at the end
-        if q_terms.size:
-            hp = torch.empty(q_terms.size, dtype=torch.int32, pin_memory=True)
-            hp.numpy()[:] = q_terms
-            dt = hp.to(self._device, non_blocking=True)
-        else:
-            dt = torch.zeros(1, dtype=torch.int32, device=self._device)
+        h_ids = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+        h_pr = torch.empty((nq, k), dtype=torch.float64, pin_memory=True)
+        h_sc = torch.empty((nq, k), dtype=torch.float32, pin_memory=True) if return_scores else None
+        for s in range(0, nq, QUERY_CHUNK):
+            e = min(nq, s + QUERY_CHUNK)
+            self._host_call(*self._stage_host(q_terms[q_off[s]:q_off[e]], q_off[s:e + 1] - q_off[s]), k,
+                            h_ids[s:e], h_sc[s:e] if return_scores else None, h_pr[s:e])
+        if return_scores:
+            return h_ids.numpy(), h_sc.numpy(), h_pr.numpy()
+        return h_ids.numpy(), h_pr.numpy()
+
+    @staticmethod
+    def _stage_host(q_terms: np.ndarray, q_off: np.ndarray):
+        """Page-locked copies of one chunk's queries (torch's caching host allocator recycles
+        the blocks from call to call)."""
+        hp = torch.empty(max(q_terms.size, 1), dtype=torch.int32, pin_memory=True)
+        hp.numpy()[:q_terms.size] = q_terms
         ho = torch.empty(q_off.size, dtype=torch.int64, pin_memory=True)
         ho.numpy()[:] = q_off
-        do = ho.to(self._device, non_blocking=True)
-        ids, sc, pr = self.retrieve_ids_device(dt, do, k)
-        outs = [ids, sc, pr] if return_scores else [ids, pr]
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
-        for h, t in zip(host, outs):
-            h.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return tuple(h.numpy() for h in host)
+        return hp, ho
+
+    def _host_call(self, hp, ho, k, h_ids, h_sc, h_pr):
+        """bb25_retrieve_batch_host on page-locked buffers (releases the GIL while it runs)."""
+        p = self._params()
+        _lib.check(_lib.lib().bb25_retrieve_batch_host(
+            self._handle, C.byref(p), hp.data_ptr(), ho.data_ptr(), ho.numel() - 1, k, h_ids.data_ptr(),
+            h_sc.data_ptr() if h_sc is not None else None, h_pr.data_ptr()))
 
     def _retrieve_large_k(self, q_terms, q_off, k, return_scores):
-        """k beyond the fused kernel's limit: dense scores and probabilities from the
-        traversal kernel, then a full device sort of (score desc, id asc) keys."""
+        """k beyond the candidate kernels' limit: the dense guaranteed path of the library, one
+        query at a time (dense scores, exact top-k of the whole vector, dense posterior); beyond
+        its own limit a full device sort of (score desc, id asc) keys."""
         nq = len(q_off) - 1
         ids = np.empty((nq, k), dtype=np.int64)
         sc = np.empty((nq, k), dtype=np.float32)
         pr = np.empty((nq, k), dtype=np.float64)
+        if k <= MAX_DENSE_K:
+            d_ids = torch.empty((nq, k), dtype=torch.int64, device=self._device)
+            d_sc = torch.empty((nq, k), dtype=torch.float32, device=self._device)
+            d_pr = torch.empty((nq, k), dtype=torch.float64, device=self._device)
+            p = self._params()
+            for i in range(nq):
+                t = np.ascontiguousarray(q_terms[q_off[i]:q_off[i + 1]], dtype=np.int32)
+                _lib.check(_lib.lib().bb25_retrieve_one_dense(
+                    self._handle, C.byref(p), t.ctypes.data, t.size, k, d_ids[i].data_ptr(), d_sc[i].data_ptr(),
+                    d_pr[i].data_ptr(), _lib.stream_ptr()))
+            ids, sc, pr = d_ids.cpu().numpy(), d_sc.cpu().numpy(), d_pr.cpu().numpy()
+            return (ids, sc, pr) if return_scores else (ids, pr)
         inv = (2 ** 31 - 1) - torch.arange(self._num_docs, device=self._device, dtype=torch.int64)
         for i in range(nq):
             t = q_terms[q_off[i]:q_off[i + 1]]
@@ -376,12 +440,26 @@ class BayesianBM25Scorer:
             raise NotImplementedError(
                 "explain=True builds FusionDebugger traces (bayesian_bm25/debug.py), which is outside "
                 "the B200 hot path; run the reference's debugger on the returned ids")
-        per_q = [self._term_ids(q) for q in query_tokens]
-        off = np.zeros(len(per_q) + 1, dtype=np.int64)
-        if per_q:
-            np.cumsum([len(q) for q in per_q], out=off[1:])
-        flat = np.concatenate(per_q).astype(np.int32) if per_q and off[-1] > 0 else np.zeros(0, dtype=np.int32)
-        return self.retrieve_ids(flat, off, k)
+        nq = len(query_tokens)
+        if nq < 2 * PIPELINE_MIN_CHUNK or k > MAX_DEVICE_K or k > self._num_docs:
+            flat, off = self._term_ids_batch(query_tokens)
+            return self.retrieve_ids(flat, off, k)
+        # Large batches: the token -> id mapping of chunk i+1 (Python dict lookups, ~2.5 us per query)
+        # runs on this thread while a worker thread sits in the C call for chunk i (ctypes drops the
+        # GIL), so the host-side mapping is hidden behind the device work.
+        step = max(PIPELINE_MIN_CHUNK, -(-nq // PIPELINE_CHUNKS))
+        h_ids = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+        h_pr = torch.empty((nq, k), dtype=torch.float64, pin_memory=True)
+        pending = None
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            for s in range(0, nq, step):
+                e = min(nq, s + step)
+                staged = self._stage_host(*self._term_ids_batch(query_tokens[s:e]))
+                if pending is not None:
+                    pending.result()
+                pending = pool.submit(self._host_call, *staged, k, h_ids[s:e], None, h_pr[s:e])
+            pending.result()
+        return h_ids.numpy(), h_pr.numpy()
 
     def index_info(self) -> dict:
         """Sizes of the device index (bb25_index_info / bb25_index_table_info)."""
@@ -409,6 +487,9 @@ class BayesianBM25Scorer:
         rq, wi = C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().bb25_retrieve_route_stats(self._handle, C.byref(rq), C.byref(wi)))
         out["routed_queries"], out["candidate_items"] = rq.value, wi.value
+        sy, bad, dn = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().bb25_retrieve_sync_stats(self._handle, C.byref(sy), C.byref(bad), C.byref(dn)))
+        out["host_syncs"], out["repaired_queries"], out["dense_fallback_queries"] = sy.value, bad.value, dn.value
         return out
 
     def set_pruning(self, level: int) -> None:

@@ -79,11 +79,16 @@ class ShardedRetriever:
     default is 1; larger batches or slower links shift that balance.
     """
 
-    def __init__(self, scorer, group=None, profile: bool = False, n_chunks: int = 1):
+    def __init__(self, scorer, group=None, profile: bool = False, n_chunks: int = 1, exchange: str = "sliced",
+                 threshold_exchange: bool = True):
+        if exchange not in ("sliced", "allgather"):
+            raise ValueError(f"exchange must be 'sliced' or 'allgather', got {exchange!r}")
         self.scorer = scorer
         self.group = group
         self.profile = profile
         self.n_chunks = max(1, int(n_chunks))
+        self.exchange = exchange
+        self.threshold_exchange = bool(threshold_exchange)
         self.timing = {"local_ms": 0.0, "gather_ms": 0.0, "merge_ms": 0.0, "calls": 0}
         self._comm_stream = None
         self._stats: dict = {}
@@ -107,10 +112,10 @@ class ShardedRetriever:
         dist.all_gather_into_tensor(buf, packed, group=self.group)
         return merge_packed_device(buf.view((world,) + tuple(packed.shape)))
 
-    def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int):
+    def retrieve_ids_device(self, q_terms: torch.Tensor, q_off: torch.Tensor, k: int, host_off=None):
         sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
         if not sharded:
-            out = self.scorer.retrieve_ids_device(q_terms, q_off, k)
+            out = self.scorer.retrieve_ids_device(q_terms, q_off, k, host_off=host_off)
             self._add_stats(reset=True)
             return out
         nq = q_off.numel() - 1
@@ -119,7 +124,7 @@ class ShardedRetriever:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None
             if ev:
                 ev[0].record()
-            ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k)
+            ids, sc, pr = self.scorer.retrieve_ids_device(q_terms, q_off, k, host_off=host_off)
             self._add_stats(reset=True)
             if ev:
                 ev[1].record()

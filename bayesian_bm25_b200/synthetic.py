@@ -100,6 +100,24 @@ def zipf_queries(n_queries: int, vocab_size: int, seed: int):
     return terms, off
 
 
+def zipf_pseudo_queries(n_docs: int, vocab_size: int, avg_doc_len: float, seed: int, min_len: int = 5,
+                        n_sample: int = 50, n_tokens: int = 5) -> list[np.ndarray]:
+    """The pseudo-queries BayesianBM25Scorer.index() draws (scorer.py:295-311: the first five tokens
+    of 50 documents picked by default_rng(42)) for the corpus zipf_csc(n_docs, ..., seed) encodes,
+    regenerated from the counter-based token hash without materialising the corpus."""
+    dl = zipf_doc_lengths(n_docs, avg_doc_len, seed, min_len)
+    offs = np.zeros(n_docs + 1, dtype=np.int64)
+    np.cumsum(dl, out=offs[1:])
+    docs = np.random.default_rng(42).choice(n_docs, size=min(n_docs, n_sample), replace=False)
+    cdf = torch.from_numpy(zipf_cdf(vocab_size))
+    out = []
+    for d in docs:
+        pos = torch.arange(int(offs[d]), int(offs[d]) + min(n_tokens, int(dl[d])), dtype=torch.int64)
+        term = torch.searchsorted(cdf, hash_uniform(seed, pos)).clamp_(max=vocab_size - 1)
+        out.append(term.numpy().astype(np.int32))
+    return out
+
+
 def zipf_csc(n_docs: int, vocab_size: int, avg_doc_len: float, seed: int, device, k1=1.2, b=0.75,
              method="lucene", min_len: int = 5, n_buckets: int | None = None) -> dict:
     """Synthetic corpus -> CSC tensors on `device` (term ids are Zipf ranks).

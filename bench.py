@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the Bayesian-BM25 query-time hot path on B200.
 
-Workload (BASELINE.json configs[1]/[2]): MS-MARCO-passage-shaped synthetic corpus,
+Default workload (BASELINE.json configs[1]/[2]): MS-MARCO-passage-shaped synthetic corpus,
 8.8 M docs, 30 k-term Zipf vocabulary, a 10 k-query batch, top-1000 calibrated
-probabilities.  One "step" = one pass of the whole batch through
-BayesianBM25Scorer.retrieve (traversal + posterior + top-k [+ all-gather merge]).
+probabilities, base_rate="auto".  One "step" = one pass of the whole batch through
+BayesianBM25Scorer.retrieve (traversal + posterior + top-k [+ sharded exchange and merge]).
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference        # CPU arm: oracle port on all host cores
+    python bench.py --config 4 | --config 5 # hybrid BM25+cosine top-100 / two-field top-10 on 50 M docs
 
 Prints ONE JSON line (see the task contract for the keys).
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import io
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -30,7 +34,10 @@ sys.path.insert(0, ROOT)
 METRIC = "queries/sec (top-1000 calibrated probs, 8.8M docs)"
 N_DOCS, VOCAB, AVG_LEN, N_QUERIES, TOP_K = 8_800_000, 30_000, 56.0, 10_000, 1000
 CORPUS_SEED, QUERY_SEED = 42, 43
-ALPHA, BETA, BASE_RATE = 2.0, 0.2, 0.045  # fixed transform constants (index-time estimation is not the timed path)
+NCU_METRICS = ("dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum,"
+               "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,"
+               "lts__throughput.avg.pct_of_peak_sustained_elapsed,"
+               "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active")
 
 
 def _env_int(name, default):
@@ -98,15 +105,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per traversal launch from the committed ncu summary, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("tile_kernel_dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+def measure_l2_peak(device_index: int) -> dict:
+    """L2 -> SM streaming-read ceiling, measured now with libbb25's own microkernel (a 48 MB buffer
+    read 40 times per launch by every SM: resident in the 126 MB L2), and the HBM read rate of the
+    same kernel over a 4 GB buffer."""
+    import ctypes as C
+    from bayesian_bm25_b200 import _lib
+    out = {}
+    for name, nbytes, iters in (("l2_read_gbs", 48 << 20, 40), ("hbm_read_gbs", 4 << 30, 1)):
+        g, ms = C.c_double(), C.c_double()
+        _lib.check(_lib.lib().bb25_measure_read_bandwidth(device_index, nbytes, iters, 5, C.byref(g), C.byref(ms)))
+        out[name] = g.value
+    return out
 
 
 def build_corpus(device, n_docs):
@@ -119,15 +129,49 @@ def algorithmic_bytes(df: np.ndarray, q_terms: np.ndarray, n_queries: int, k: in
     return int(df[q_terms].sum()) * 8 + n_queries * k * 20
 
 
-def cpu_baseline(host_csc, q_terms, q_off, k, sample_q, threads=0):
+def cpu_baseline(host_csc, params3, q_terms, q_off, k, sample_q, threads=0):
     from oracle import coracle
-    params = coracle.make_params(ALPHA, BETA, BASE_RATE)
+    params = coracle.make_params(*params3)
     qt = q_terms[: q_off[sample_q]]
     qo = q_off[: sample_q + 1]
     t0 = time.perf_counter()
     _, _, _, used = coracle.retrieve_batch(host_csc, params, qt, qo, k, n_threads=threads)
     dt = time.perf_counter() - t0
     return sample_q / dt, used, dt
+
+
+def literal_reference_config1() -> dict:
+    """the reference's own BayesianBM25Scorer (baseline/_ref, installed from the
+    unmodified reference) over the bm25s stand-in of oracle/bm25s_equiv.py, on BASELINE configs[0]
+    (10 k docs, 100 queries, k = 10, base_rate auto), timed by the reference's own
+    benchmarks/scalability.py:measure_retrieve -- one thread, one query per call, as the reference runs."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "bayesian_bm25")):
+        return {"unavailable": "baseline/_ref is not installed (pip install --target baseline/_ref <reference>)"}
+    try:
+        import importlib.metadata as md
+        orig = md.version
+        md.version = lambda name: "0.12.1" if name == "bayesian-bm25" else orig(name)
+        from oracle import bm25s_equiv
+        sys.modules.setdefault("bm25s", bm25s_equiv)
+        sys.path.insert(0, ref)
+        from bayesian_bm25.scorer import BayesianBM25Scorer as RefScorer
+        from benchmarks.scalability import generate_synthetic_corpus, measure_retrieve
+        corpus, queries = generate_synthetic_corpus(10_000, 10_000, 100, np.random.default_rng(42))
+        sc = RefScorer(k1=1.2, b=0.75, method="lucene", base_rate="auto")
+        t0 = time.perf_counter()
+        sc.index(corpus, show_progress=False)
+        t_index = time.perf_counter() - t0
+        measure_retrieve(sc, queries[:5], k=10)
+        m = measure_retrieve(sc, queries, k=10)
+        return {"config": "BASELINE configs[0]: 10k docs, 10k-term Zipf vocab, 100 queries, k=10, base_rate auto",
+                "how": "reference scorer.py (baseline/_ref) over oracle/bm25s_equiv.py, benchmarks/scalability.py:measure_retrieve",
+                "threads": 1, "queries_per_s": 1000.0 / m["mean_ms"], "index_s": round(t_index, 2), **m}
+    except Exception as e:  # the literal leg is a reported extra, never a reason to lose the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        if sys.path and sys.path[0] == ref:
+            sys.path.pop(0)
 
 
 def run_reference(args):
@@ -147,11 +191,12 @@ def run_reference(args):
     from oracle import coracle
     cores = coracle.max_threads()
     sample = min(args.queries, max(256, 24 * cores))
+    p3 = (2.0, 0.2, 0.045)  # the CPU arm's cost does not depend on the transform constants
     for _ in range(args.warmup):
-        cpu_baseline(host, q_terms, q_off, args.k, min(sample, cores))
+        cpu_baseline(host, p3, q_terms, q_off, args.k, min(sample, cores))
     times = []
     for _ in range(args.steps):
-        qps, used, dt = cpu_baseline(host, q_terms, q_off, args.k, sample)
+        qps, used, dt = cpu_baseline(host, p3, q_terms, q_off, args.k, sample)
         times.append(dt)
     total = sum(times)
     value = sample * args.steps / total
@@ -161,11 +206,95 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n_docs} docs, {VOCAB}-term Zipf vocab, top-{args.k}; each step = {sample} queries of the {args.queries}-query batch"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": used, "kind": "port",
-                         "sample": f"{sample} queries/step x {args.steps} steps, oracle/bb25_oracle.c orc_retrieve_batch, {used} threads"},
+                         "sample": f"{sample} queries/step x {args.steps} steps, oracle/bb25_oracle.c orc_retrieve_batch, {used} threads",
+                         "literal": literal_reference_config1()},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# ncu traffic probe: the measured DRAM / L2 bytes of the traversal kernel for THIS build and
+# THIS shard size (counters, not timings), collected by a child run of the same workload
+# ---------------------------------------------------------------------------------------
+def parse_ncu_csv(text: str, kernel_substr: str):
+    rows = []
+    start = text.find('"ID"')
+    if start < 0:
+        return rows
+    per = {}
+    for r in csv.DictReader(io.StringIO(text[start:])):
+        if kernel_substr not in r.get("Kernel Name", ""):
+            continue
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except (ValueError, KeyError):
+            continue
+        unit = r.get("Metric Unit", "")
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "us": 1e3, "ms": 1e6, "s": 1e9,
+                 "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1.0)
+        per.setdefault(int(r["ID"]), {})[r["Metric Name"]] = v * scale
+    return [per[i] for i in sorted(per)]
+
+
+def traffic_probe(args, shard: str, params3, timeout_s: int = 420) -> dict:
+    ncu = shutil.which("ncu")
+    if not ncu or args.no_probe:
+        return {"unavailable": "ncu not found" if not ncu else "disabled by --no-probe"}
+    cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "-k", "regex:block_kernel", "--csv",
+           sys.executable, os.path.abspath(__file__), "--probe-child", "--docs", str(args.docs), "--queries",
+           str(args.queries), "--k", str(args.k), "--shard", shard, "--probe-params",
+           ",".join(repr(float(x)) for x in params3)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR",
+                                                             "MASTER_PORT", "LOCAL_WORLD_SIZE", "GROUP_RANK",
+                                                             "TORCHELASTIC_RUN_ID")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"ncu probe timed out after {timeout_s} s"}
+    launches = parse_ncu_csv(r.stdout, "block_kernel")
+    if r.returncode != 0 or not launches:
+        return {"unavailable": f"ncu probe failed (rc={r.returncode}): {(r.stderr or r.stdout)[-300:]}"}
+    # the child runs the batch twice; the second half of the launches is the warmed-up step
+    step = launches[len(launches) // 2:]
+    def tot(name):
+        return float(sum(l.get(name, 0.0) for l in step))
+    dur_ns = tot("gpu__time_duration.sum")
+    big = max(step, key=lambda l: l.get("gpu__time_duration.sum", 0.0))
+    return {
+        "source": "ncu child run of this bench (same build, same shard), block_kernel launches of one exhaustive step",
+        "launches": len(step), "dram_bytes": tot("dram__bytes_read.sum") + tot("dram__bytes_write.sum"),
+        "l2_bytes": tot("lts__t_bytes.sum"), "kernel_ns_under_ncu": dur_ns,
+        "largest_launch": {
+            "ms_under_ncu": big.get("gpu__time_duration.sum", 0.0) / 1e6,
+            "lsu_wavefronts_pct": big.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            "lts_throughput_pct": big.get("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+            "issue_active_pct": big.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "warps_active_pct": big.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        },
+    }
+
+
+def probe_child(args):
+    """Runs under ncu: the exhaustive batch twice on one GPU with the given transform constants."""
+    import torch
+    from bayesian_bm25_b200 import BayesianBM25Scorer, sharded, synthetic
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    csc = build_corpus(dev, args.docs)
+    r, w = (int(x) for x in args.shard.split("/"))
+    if w > 1:
+        csc = sharded.local_shard(csc, r, w)
+    a, b, br = (float(x) for x in args.probe_params.split(","))
+    sc = BayesianBM25Scorer(k1=1.2, b=0.75, method="lucene", alpha=a, beta=b, base_rate=br)
+    sc.index_from_csc(csc)
+    sc.set_pruning(0)
+    q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, QUERY_SEED)
+    dt, do = torch.from_numpy(q_terms).to(dev), torch.from_numpy(q_off).to(dev)
+    for _ in range(2):
+        sc.retrieve_ids_device(dt, do, args.k, host_off=q_off)
+    torch.cuda.synchronize()
 
 
 def main():
@@ -174,14 +303,23 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--docs", type=int, default=N_DOCS)
-    ap.add_argument("--queries", type=int, default=N_QUERIES)
-    ap.add_argument("--k", type=int, default=TOP_K)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json configs: 2 = headline (1/2/4/8 GPUs), 4 = hybrid top-100, 5 = two-field 50M top-10")
+    ap.add_argument("--docs", type=int, default=0)
+    ap.add_argument("--queries", type=int, default=0)
+    ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-probe", action="store_true", help="skip the ncu traffic probe")
     ap.add_argument("--prune-level", type=int, default=3, help="pruning level of the extra 'pruned' pass")
     ap.add_argument("--shard-chunks", type=int, default=1,
-                    help="query sub-batches pipelined against the all-gather (N>1); 1 measured best at Q=10k (profiles/r01)")
+                    help="query sub-batches pipelined against the exchange (N>1); 1 measured best at Q=10k (profiles/r01)")
+    ap.add_argument("--exchange", default="sliced", choices=["sliced", "allgather"],
+                    help="N>1: query-sliced all-to-all exchange (default) or the round-1 all-gather + full merge")
+    ap.add_argument("--no-thr-exchange", action="store_true", help="N>1: do not exchange thresholds between block groups")
+    ap.add_argument("--probe-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--shard", default="0/1", help=argparse.SUPPRESS)
+    ap.add_argument("--probe-params", default="2.0,0.2,0.045", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -189,6 +327,19 @@ def main():
     if not os.path.exists(entry.SO):
         entry.build()
 
+    if args.config in (4, 5):
+        import bench_fused
+        if args.impl == "reference":
+            bench_fused.run_reference(args)
+        else:
+            bench_fused.run(args)
+        return
+    args.docs = args.docs or N_DOCS
+    args.queries = args.queries or N_QUERIES
+    args.k = args.k or TOP_K
+    if args.probe_child:
+        probe_child(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -214,20 +365,32 @@ def main():
     host_csc = None
     if rank == 0 and not args.no_cpu:
         host_csc = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in csc.items()}
+    # alpha / beta / base_rate as BayesianBM25Scorer.index() estimates them (base_rate="auto",
+    # scorer.py:287-311): pseudo-queries scored on the FULL index, so every shard uses the same scalars
+    pseudo = synthetic.zipf_pseudo_queries(args.docs, VOCAB, AVG_LEN, CORPUS_SEED)
+    scorer = BayesianBM25Scorer(k1=1.2, b=0.75, method="lucene", base_rate="auto")
+    scorer.index_from_csc(csc, pseudo_queries=pseudo)
+    tr = scorer.transform
+    params3 = (float(tr.alpha), float(tr.beta), float(tr.base_rate))
     if world > 1:
-        csc = sharded.local_shard(csc, rank, world)
-    scorer = BayesianBM25Scorer(k1=1.2, b=0.75, method="lucene", alpha=ALPHA, beta=BETA, base_rate=BASE_RATE)
-    scorer.index_from_csc(csc)
+        del scorer
+        torch.cuda.empty_cache()
+        scorer = BayesianBM25Scorer(k1=1.2, b=0.75, method="lucene", alpha=params3[0], beta=params3[1], base_rate=params3[2])
+        scorer.index_from_csc(sharded.local_shard(csc, rank, world))
     del csc
     torch.cuda.empty_cache()
-    retr = sharded.ShardedRetriever(scorer, n_chunks=args.shard_chunks)
+    vocab_tokens = [f"term_{i}" for i in range(VOCAB)]
+    scorer.set_vocabulary(vocab_tokens)
+    retr = sharded.ShardedRetriever(scorer, n_chunks=args.shard_chunks, exchange=args.exchange,
+                                    threshold_exchange=not args.no_thr_exchange)
     q_terms, q_off = synthetic.zipf_queries(args.queries, VOCAB, QUERY_SEED)
+    query_tokens = [[vocab_tokens[t] for t in q_terms[q_off[i]:q_off[i + 1]]] for i in range(args.queries)]
     d_terms = torch.from_numpy(q_terms).to(dev)
     d_off = torch.from_numpy(q_off).to(dev)
     t_build = time.perf_counter() - t_build
 
     def step():
-        return retr.retrieve_ids_device(d_terms, d_off, args.k)
+        return retr.retrieve_ids_device(d_terms, d_off, args.k, host_off=q_off)
 
     def barrier():
         if world > 1:
@@ -235,23 +398,29 @@ def main():
         torch.cuda.synchronize()
 
     def e2e_step():
-        """The call a user makes: host buffers in, host buffers out (H2D + D2H inside)."""
+        """The call a user makes: BayesianBM25Scorer.retrieve(list[list[str]], k) -- token strings
+        in, host arrays out (token -> id mapping, H2D and D2H inside)."""
+        if world == 1:
+            return scorer.retrieve(query_tokens, args.k)
+        return retr.retrieve(query_tokens, args.k)  # every rank maps its own copy of the queries; results on rank 0
+
+    def e2e_ids_step():
         if world == 1:
             return scorer.retrieve_ids(q_terms, q_off, args.k)
-        hp = torch.empty(q_terms.size, dtype=torch.int32, pin_memory=True)
-        hp.numpy()[:] = q_terms
-        ho = torch.empty(q_off.size, dtype=torch.int64, pin_memory=True)
-        ho.numpy()[:] = q_off
-        ids, sc, pr = retr.retrieve_ids_device(hp.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), args.k)
-        if rank != 0:  # the merged result is identical on every rank; the caller lives on rank 0
-            torch.cuda.current_stream().synchronize()
-            return None
-        h_ids = torch.empty(ids.shape, dtype=ids.dtype, pin_memory=True)
-        h_pr = torch.empty(pr.shape, dtype=pr.dtype, pin_memory=True)
-        h_ids.copy_(ids, non_blocking=True)
-        h_pr.copy_(pr, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return h_ids.numpy(), h_pr.numpy()
+        return retr.retrieve_ids(q_terms, q_off, args.k)
+
+    def timed_wall(fn):
+        for _ in range(3):  # lets torch's pinned-host allocator settle on reusable blocks
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te[0])
 
     def measure(level: int, sample_clocks: bool):
         """W warm-up + K timed steps at one pruning level: device-resident timing (CUDA
@@ -266,14 +435,15 @@ def main():
         launches0 = _lib.lib().bb25_launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {"traverse_ms": 0.0, "traverse_launches": 0, "rerun_queries": 0, "units": 0, "units_skipped": 0,
-               "units_maxscore": 0, "routed_queries": 0, "candidate_items": 0}
+               "units_maxscore": 0, "routed_queries": 0, "candidate_items": 0, "host_syncs": 0,
+               "repaired_queries": 0, "dense_fallback_queries": 0}
         barrier()
         ev0.record()
         for _ in range(args.steps):
             out = step()
             st = retr.stats()
             for key in acc:
-                acc[key] += st[key]
+                acc[key] += st.get(key, 0)
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -282,35 +452,33 @@ def main():
         t = torch.tensor([ms, acc["traverse_ms"]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        for _ in range(3):  # lets torch's pinned-host allocator settle on reusable blocks
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = timed_wall(e2e_step)
+        e2e_ids_s = timed_wall(e2e_ids_step)
         return {"ms": float(t[0]), "trav_ms": float(t[1]), "launches": launches, "clocks": clocks,
-                "e2e_s": float(te[0]), "out": out, **{k_: v / args.steps for k_, v in acc.items() if k_ != "traverse_ms"}}
+                "e2e_s": e2e_s, "e2e_ids_s": e2e_ids_s, "out": out,
+                **{k_: v / args.steps for k_, v in acc.items() if k_ != "traverse_ms"}}
 
     # headline: exhaustive traversal (every posting of every query term is visited, like the
     # reference); then the same batch with the library's default dynamic pruning (exact)
     ex = measure(0, sample_clocks=True)
     shard_timing = None
-    if world > 1:  # one extra, untimed, unpipelined pass that times the phases separately
+    if world > 1:  # one extra, untimed pass that times the phases separately
         retr.profile = True
         step()
         barrier()
         step()
         shard_timing = {k_: v / max(1, retr.timing["calls"]) for k_, v in retr.timing.items() if k_ != "calls"}
+        t = torch.tensor([shard_timing[k_] for k_ in sorted(shard_timing)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        shard_timing = {k_: float(v) for k_, v in zip(sorted(shard_timing), t)}
+        shard_timing["what"] = "max over ranks, one profiled (event-separated) pass"
         retr.profile = False
     pr = measure(args.prune_level, sample_clocks=False)
     same = all(bool(torch.equal(x, y)) for x, y in zip(ex["out"], pr["out"]))
     out = ex["out"]
     ms, trav_ms_max, launches, clocks, e2e_s = ex["ms"], ex["trav_ms"], ex["launches"], ex["clocks"], ex["e2e_s"]
     trav_launches, reruns = ex["traverse_launches"] * args.steps, ex["rerun_queries"] * args.steps
+    n_tok = int(q_off[-1])
     h2d = int(q_terms.nbytes + q_off.nbytes)
     d2h = int(args.queries * args.k * (8 + 8))
 
@@ -319,25 +487,73 @@ def main():
         alg_bytes_step = algorithmic_bytes(df_full, q_terms, args.queries, args.k)
         # every rank scans 1/world of each posting list; the roofline line is per GPU
         alg_bytes_gpu = alg_bytes_step / world
-        peak, peak_src = measured_peak_gbs()
-        achieved = alg_bytes_gpu * args.steps / (trav_ms_max / 1000.0) / 1e9 if trav_ms_max > 0 else 0.0
+        hbm_peak, peak_src = measured_peak_gbs()
+        kernel_s = trav_ms_max / args.steps / 1000.0
+        effective = alg_bytes_gpu / kernel_s / 1e9 if kernel_s > 0 else 0.0
+        peaks = measure_l2_peak(local)
+        probe = traffic_probe(args, f"0/{world}", params3)
+        roof = {
+            "kernel": "bb25::block_kernel (order-free posting traversal, exhaustive; candidates re-scored in query order by select_kernel)",
+            "kernel_ms_per_step": trav_ms_max / args.steps, "kernel_launches_per_step": trav_launches / args.steps,
+            "effective": {"value": effective, "unit": "GB/s",
+                          "what": "ALGORITHMIC bytes (SURVEY 8d: sum_q sum_t df(t)*8 B + k*20 B, per GPU) / summed traversal-kernel time "
+                                  "(CUDA events in libbb25 on the call's stream); not a fraction of any peak: every block's index slice is "
+                                  "shared by all warps through L2, so one DRAM byte serves many queries",
+                          "vs_hbm_peak": effective / hbm_peak},
+            "algorithmic_bytes_per_step_per_gpu": alg_bytes_gpu,
+            "peaks": {"hbm_copy_gbs": hbm_peak, "hbm_copy_source": peak_src, "l2_read_gbs": peaks["l2_read_gbs"],
+                      "hbm_read_gbs": peaks["hbm_read_gbs"],
+                      "l2_hbm_read_source": "measured in this run: libbb25 stream_read_kernel (bb25_measure_read_bandwidth), 48 MB x40 / 4 GB x1, best of 5"},
+        }
+        if "unavailable" not in probe:
+            dram_gbs = probe["dram_bytes"] / kernel_s / 1e9
+            l2_gbs = probe["l2_bytes"] / kernel_s / 1e9
+            lsu = probe["largest_launch"].get("lsu_wavefronts_pct")
+            fr = {"dram": dram_gbs / hbm_peak, "l2": l2_gbs / peaks["l2_read_gbs"],
+                  "lsu_wavefronts": (lsu / 100.0) if lsu is not None else None}
+            bound = max((k_ for k_ in fr if fr[k_] is not None), key=lambda k_: fr[k_])
+            label = {"dram": "hbm", "l2": "l2", "lsu_wavefronts": "l1tex-lsu"}[bound]
+            if bound == "dram":
+                ach, pk, unit = dram_gbs, hbm_peak, "GB/s"
+            elif bound == "l2":
+                ach, pk, unit = l2_gbs, peaks["l2_read_gbs"], "GB/s"
+            else:
+                ach, pk, unit = lsu, 100.0, "% of peak L1 data-pipe LSU wavefronts (ncu, largest launch)"
+            roof.update({"bound": label, "achieved": ach, "peak": pk, "unit": unit, "frac": fr[bound],
+                         "traffic": probe["dram_bytes"] / max(1, probe["launches"]),
+                         "fractions": fr, "dram_gbs": dram_gbs, "l2_gbs": l2_gbs, "probe": probe,
+                         "note": "three measured fractions: DRAM bytes/s over the HBM copy peak, L2 bytes/s over the measured L2 read peak, "
+                                 "LSU data-pipe wavefronts as ncu reports them; `bound` names the largest.  Byte counters come from the ncu "
+                                 "child run, the time from CUDA events of the un-profiled timed region"})
+        else:
+            roof.update({"bound": "l1tex-lsu", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                         "probe": probe,
+                         "note": "no live counter probe in this run; see profiles/r02 for the ncu capture of this build "
+                                 "(DRAM ~2 % of peak, L1 data-pipe LSU wavefronts the busiest unit)"})
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": (f"{args.docs} docs, {VOCAB}-term Zipf vocab (avg len {AVG_LEN:g}), nnz {nnz_full}, "
-                             f"{args.queries}-query batch (3-5 terms), top-{args.k}, exhaustive traversal"),
-                "parallelism": f"doc-range shards x{world}" + (" + NCCL all-gather merge" if world > 1 else ""),
+                             f"{args.queries}-query batch (3-5 terms), top-{args.k}, exhaustive traversal, base_rate=auto"),
+                "parallelism": f"doc-range shards x{world}" + (f" + NCCL {args.exchange} exchange and device merge" if world > 1 else ""),
                 "cache": "inputs larger than L2 (CSC index %.2f GB per GPU, 126 MB L2)" % (nnz_full * 8 / world / 1e9),
                 "probabilities": "fp64 posterior fused on device", "index_build_s": round(t_build, 1),
+                "transform": {"alpha": params3[0], "beta": params3[1], "base_rate": params3[2],
+                              "how": "estimated by index_from_csc(pseudo_queries=...) as scorer.py:287-364 does (base_rate='auto')"},
                 "threshold_reruns_per_step": reruns / args.steps,
+                "host_syncs_per_step": ex["host_syncs"], "repaired_queries_per_step": ex["repaired_queries"],
+                "dense_fallback_queries_per_step": ex["dense_fallback_queries"],
                 "kernel": os.environ.get("BB25_KERNEL", "block"), "pruning_level": 0,
             },
             "clocks": clocks,
             "sharded_breakdown_ms_per_call": shard_timing,
             "e2e": {"value": args.queries * args.steps / e2e_s, "unit": "queries/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "BayesianBM25Scorer.retrieve(list[list[str]], k): %d token strings mapped to ids on the host inside the timed region" % n_tok,
+                    "retrieve_ids_value": args.queries * args.steps / ex["e2e_ids_s"],
+                    "retrieve_ids_call": "retrieve_ids(term ids) -> bb25_retrieve_batch_host (page-locked host buffers in and out)"},
             "gpu_launches": launches,
             "pruned": {
                 "what": "same batch with the library's default dynamic pruning (bb25_index_set_pruning level %d: "
@@ -345,37 +561,33 @@ def main():
                         "to the exhaustive pass" % args.prune_level,
                 "value": args.queries * args.steps / (pr["ms"] / 1000.0), "unit": "queries/s",
                 "ms_per_step": pr["ms"] / args.steps, "kernel_ms_per_step": pr["trav_ms"] / args.steps,
-                "e2e_value": args.queries * args.steps / pr["e2e_s"], "results_identical": same,
+                "e2e_value": args.queries * args.steps / pr["e2e_s"],
+                "e2e_retrieve_ids_value": args.queries * args.steps / pr["e2e_ids_s"], "results_identical": same,
                 "block_docs": 1024, "units_per_step": pr["units"], "units_skipped_per_step": pr["units_skipped"],
                 "units_maxscore_per_step": pr["units_maxscore"],
                 "queries_routed_to_candidate_path_per_step": pr["routed_queries"],
-                "candidate_items_per_step": pr["candidate_items"],
+                "candidate_items_per_step": pr["candidate_items"], "host_syncs_per_step": pr["host_syncs"],
             },
-            "roofline": {
-                "bound": "hbm", "kernel": "bb25::block_kernel (order-free posting traversal, exhaustive; candidates re-scored in query order by select_kernel)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": ncu_traffic_per_launch(),
-                "algorithmic_bytes_per_step_per_gpu": alg_bytes_gpu,
-                "kernel_ms_per_step": trav_ms_max / args.steps, "kernel_launches_per_step": trav_launches / args.steps,
-                "note": "achieved = sum_q sum_t df(t)*8B (+k*20B) / summed traversal-kernel time (CUDA events in libbb25); "
-                        "all warps share a block's index slice through L2, so DRAM traffic is far below the algorithmic "
-                        "bytes and the figure can exceed the HBM peak (DESIGN.md 4.1); the exact re-scoring of the "
-                        "emitted candidates runs in select_kernel and is part of ms_per_step, not of this kernel time",
-            },
+            "roofline": roof,
         }
         if host_csc is not None:
             from oracle import coracle
             cores = coracle.max_threads()
             sample = args.cpu_sample or min(args.queries, max(256, 24 * cores))
-            v, used, dt = cpu_baseline(host_csc, q_terms, q_off, args.k, sample)
+            v, used, dt = cpu_baseline(host_csc, params3, q_terms, q_off, args.k, sample)
             line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": used, "kind": "port",
-                                    "sample": f"first {sample} queries of the batch, oracle/bb25_oracle.c, {dt:.1f} s wall"}
-            # spot-check the timed output against the oracle on the sampled queries
-            o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host_csc, coracle.make_params(ALPHA, BETA, BASE_RATE),
-                                                          q_terms[: q_off[8]], q_off[:9], args.k)
-            ids8 = out[0][:8].cpu().numpy()
-            line["parity_spot_check"] = bool(np.array_equal(ids8, o_ids) and
-                                             np.max(np.abs(out[2][:8].cpu().numpy() - o_pr)) < 1e-9)
+                                    "sample": f"first {sample} queries of the batch, oracle/bb25_oracle.c, {dt:.1f} s wall",
+                                    "literal": literal_reference_config1()}
+            # spot-check the timed output against the oracle: ids, fp32 scores (bit-exact), probabilities
+            ns = min(64, args.queries)
+            o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host_csc, coracle.make_params(*params3),
+                                                          q_terms[: q_off[ns]], q_off[: ns + 1], args.k)
+            ok_ids = bool(np.array_equal(out[0][:ns].cpu().numpy(), o_ids))
+            ok_sc = bool(np.array_equal(out[1][:ns].cpu().numpy().view(np.uint32), o_sc.view(np.uint32)))
+            err_pr = float(np.max(np.abs(out[2][:ns].cpu().numpy() - o_pr)))
+            line["parity_spot_check"] = bool(ok_ids and ok_sc and err_pr < 1e-9)
+            line["parity_spot_check_detail"] = {"queries": ns, "ids_equal": ok_ids, "scores_bit_equal": ok_sc,
+                                                "max_abs_prob_err": err_pr}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

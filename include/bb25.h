@@ -58,6 +58,11 @@ int bb25_version(void);
 unsigned long long bb25_launch_count(void);
 /* number of CUDA devices visible (0 when there is none / no driver) */
 int bb25_device_count(void);
+/* Measured ceilings for the roofline lines (no reference counterpart): best-of-`reps` bandwidth of a
+ * streaming 128-bit read of a `bytes`-sized device buffer, read `iters` times per launch by every SM.
+ * bytes <= ~64 MB stays resident in the 126 MB L2 (L2 -> SM bandwidth); bytes >> 126 MB reads HBM. */
+int bb25_measure_read_bandwidth(int device, int64_t bytes, int iters, int reps, double *out_gbs,
+                                double *out_ms);
 
 /* ---- index ------------------------------------------------------------- */
 
@@ -124,11 +129,44 @@ int bb25_retrieve_batch(bb25_index *idx, const bb25_params *params, const int32_
                         const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
                         float *out_scores, double *out_probs, void *stream);
 
+/* The same call when the caller knows the batch's extent on the host (q_off[0] and
+ * q_off[Q] - q_off[0]): nothing is read back before the work is enqueued, and the whole batch --
+ * threshold repairs included -- costs ONE stream synchronisation, at the end (the report that
+ * carries the input-validation flag and the statistics).  bb25_retrieve_batch reads the two
+ * offsets from the device first (one more synchronisation). */
+int bb25_retrieve_batch_ex(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
+                           const int64_t *q_off, int64_t n_queries, int64_t term_base, int64_t n_terms_total,
+                           int k, int64_t *out_ids, float *out_scores, double *out_probs, void *stream);
+
 /* Same call with HOST buffers: copies the queries in, runs the batch, copies
- * the results out (the end-to-end path the Python wrapper uses). */
+ * the results out (the end-to-end path the Python wrapper uses).  The device staging area and
+ * the stream are owned by the handle and reused across calls; with page-locked caller buffers
+ * the copies are asynchronous and the call synchronises twice (report, results). */
 int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
                              const int64_t *q_off, int64_t n_queries, int k, int64_t *out_ids,
                              float *out_scores, double *out_probs);
+
+/* One query through the dense guaranteed path: fp32 scores of every document (bm25s get_scores,
+ * scorer.py:583), exact top-k of the whole vector by (score desc, doc id asc), probabilities from
+ * the dense posterior pass (scorer.py:603-640).  O(N); 1 <= k <= min(n_docs, 8192).  This is also
+ * what bb25_retrieve_batch falls back to for a query whose threshold refinement does not settle.
+ * q_terms: host. */
+int bb25_retrieve_one_dense(bb25_index *idx, const bb25_params *params, const int32_t *q_terms, int n_terms, int k,
+                            int64_t *out_ids /*dev [k]*/, float *out_scores /*dev [k] or NULL*/,
+                            double *out_probs /*dev [k]*/, void *stream);
+
+/* host synchronisations inside the last batch, queries that needed the host-driven repair after the
+ * enqueued repair rounds, queries that took the dense guaranteed path */
+int bb25_retrieve_sync_stats(const bb25_index *idx, int64_t *host_syncs, int64_t *repaired_queries,
+                             int64_t *dense_fallback_queries);
+
+/* Sharded retrieval: `fn` is called on the host between the block groups of a batch
+ * (group = 0, 1, ...), after the group's work has been enqueued on `stream`, so that the ranks can
+ * raise each other's thresholds (bb25_publish_quantiles / an all-gather / bb25_apply_quantiles,
+ * all stream-ordered -- the callback must not synchronise).  Return non-zero to fail the batch. */
+typedef int (*bb25_exchange_fn)(void *user, void *d_thr, void *d_cand_cnt, void *d_cand_key, int64_t n_queries,
+                                int cap, int k, int group, void *stream);
+int bb25_index_set_threshold_exchange(bb25_index *idx, bb25_exchange_fn fn, void *user);
 
 /* statistics of the last bb25_retrieve_batch on this handle: kernel launches,
  * traversal passes (1 per tile group + re-runs), re-run (query,group) units,
