@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "bb25_internal.cuh"
+#include "bb25_device.cuh"
 
 namespace bb25 {
 
@@ -69,26 +70,6 @@ struct TileMeta {
     uint8_t m_slot[MAXT];
 };
 
-__device__ __forceinline__ float4 ld_nc_f4(const float4 *p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-// Dense value rows are shared by every warp of the SM working on the same block (items are
-// block-major), so unlike the posting streams they are worth keeping in L1.
-__device__ __forceinline__ float4 ld_row_f4(const float4 *p) {
-#if defined(BB25_ROW_NOALLOC)
-    return ld_nc_f4(p);
-#else
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-#endif
-}
-
 template <bool COUNT>
 __device__ __forceinline__ void rmw1(float *acc, uint8_t *cnt, int off, float v) {
     acc[off] = __fadd_rn(acc[off], v);
@@ -96,17 +77,6 @@ __device__ __forceinline__ void rmw1(float *acc, uint8_t *cnt, int off, float v)
         unsigned c = cnt[off];
         cnt[off] = (uint8_t)(c < 255u ? c + 1u : 255u);
     }
-}
-
-__device__ __forceinline__ int ld_nc_s32(const int32_t *p) {
-    int r;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ld_nc_f32(const float *p) {
-    float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
 }
 
 // Add postings [s, s+len) of one term into the tile accumulators.  Doc ids inside a
@@ -820,19 +790,6 @@ struct BlockArgs {
 
 // per-warp shared memory: 1024 fp32 accumulators
 
-__device__ __forceinline__ long long shfl_ll(long long v, int src) {
-    int lo = __shfl_sync(0xFFFFFFFFu, (int)(v & 0xFFFFFFFFll), src);
-    int hi = __shfl_sync(0xFFFFFFFFu, (int)(v >> 32), src);
-    return ((long long)hi << 32) | (unsigned int)lo;
-}
-
-// acc[o] (+)= v.  FRESH: the accumulators are known to be all zero (first term of the
-// unit), so the read half of the read-modify-write is dropped; v + 0.0f keeps -0.0f out.
-template <bool FRESH>
-__device__ __forceinline__ void acc_add(float *acc, int o, float v) {
-    acc[o] = FRESH ? __fadd_rn(v, 0.0f) : __fadd_rn(acc[o], v);
-}
-
 // postings [s, s+len) of one term, len <= 1024, into the warp's block accumulators
 template <bool FRESH = false>
 __device__ __forceinline__ void scatter_warp(const float *__restrict__ data, const int32_t *__restrict__ indices,
@@ -889,30 +846,6 @@ __device__ __forceinline__ void dense_add_warp(const float *__restrict__ row, fl
     }
 }
 
-// postings [s, s+len) of one term into the warp's block accumulators, up to 64 postings per
-// round of loads (no alignment peel: a short slice must not cost two dependent rounds)
-template <bool FRESH>
-__device__ __forceinline__ void scatter_block(const float *__restrict__ data, const int32_t *__restrict__ indices,
-                                              long long s, int len, float *acc, int doc_base, int lane) {
-    const int32_t *ip = indices + s;
-    const float *dp = data + s;
-    for (int j0 = 0; j0 < len; j0 += 64) {
-        int d[2];
-        float v[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int j = j0 + 32 * u + lane;
-            if (j < len) {
-                d[u] = ld_nc_s32(ip + j);
-                v[u] = ld_nc_f32(dp + j);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-            if (j0 + 32 * u + lane < len) acc_add<FRESH>(acc, d[u] - doc_base, v[u]);
-    }
-}
-
 struct TermEnt {
     long long start;
     int len;
@@ -938,12 +871,6 @@ __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, int blk, 
         e.dslot = e.len > 0 ? (int)info.y : -1;
     }
     return e;
-}
-
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-    return v;
 }
 
 // emit one accumulator if it can enter the query's top-k
@@ -984,19 +911,6 @@ __device__ __noinline__ void emit_quad_relaxed(float4 v, uint32_t first_id, uint
             if (pos < (unsigned)cap) crow[pos] = make_key(bits, first_id + c, 0u);
         }
     }
-}
-
-// fp32 x 2 add (Blackwell FADD2): the same round-to-nearest result per element as two FADDs
-__device__ __forceinline__ void add_f4(float4 &v, const float4 &r) {
-    unsigned long long a0, a1, b0, b1;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(v.x), "f"(v.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(v.z), "f"(v.w));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b0) : "f"(r.x), "f"(r.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b1) : "f"(r.z), "f"(r.w));
-    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(b0));
-    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(b1));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(a0));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(a1));
 }
 
 struct PassArgs {
@@ -1625,7 +1539,6 @@ static void base_args(const bb25_index *idx, TileArgs &a) {
     a.n_docs = idx->n_docs;
 }
 
-static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // dense single-query outputs (get_scores / get_probabilities)
 __global__ void fuse_const_kernel(double *acc, int64_t n, double p, FuseSpec f) {
