@@ -31,6 +31,20 @@ def make_params(alpha, beta, base_rate=None, prior_free=False) -> Params:
                   float(base_rate) if base_rate is not None else 0.0, 1 if prior_free else 0)
 
 
+class FusedField(C.Structure):
+    """struct bb25_fused_field"""
+
+    _fields_ = [
+        ("index", C.c_void_p),
+        ("params", Params),
+        ("weight", C.c_double),
+        ("q_terms", C.c_void_p),
+        ("q_off", C.c_void_p),
+        ("term_base", C.c_int64),
+        ("n_terms_total", C.c_int64),
+    ]
+
+
 _vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
 _PP = C.POINTER(Params)
 
@@ -77,6 +91,9 @@ SIGNATURES = {
     "bb25_fuse_bm25_signal": (_i32, [_vp, _PP, _vp, _i32, _dbl, _i32, _dbl, _i32, _vp, _vp]),
     "bb25_fuse_cosine_signal": (_i32, [_i32, _vp, _i64, _dbl, _i32, _dbl, _i32, _vp, _vp]),
     "bb25_fuse_prob_signal": (_i32, [_i32, _vp, _i64, _dbl, _i32, _dbl, _i32, _vp, _vp]),
+    "bb25_retrieve_fused_batch": (_i32, [_i32, C.POINTER(FusedField), _vp, _i64, _dbl, _i32, _dbl, _i64, _i32, _vp, _vp, _vp]),
+    "bb25_fused_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_dbl)]),
     "bb25_blockmax_dense": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "bb25_blockmax_csc": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
 }

@@ -267,6 +267,9 @@ struct bb25_index {
     int64_t st_syncs = 0;           // host synchronisations inside the last retrieve_batch
     int64_t st_bad = 0;             // queries that needed the host-driven repair / ...
     int64_t st_dense_fallback = 0;  // ... the dense guaranteed path
+    // stats of the last bb25_retrieve_fused_batch whose first field is this index
+    int64_t fz_units = 0, fz_skipped = 0, fz_abandoned = 0, fz_candidates = 0, fz_fallback = 0, fz_reruns = 0, fz_syncs = 0;
+    double fz_traverse_ms = 0.0;
     // device + stream of the host-buffer entry points (grow-only, reused across calls)
     void *hs_dev = nullptr;
     size_t hs_bytes = 0;
@@ -291,5 +294,8 @@ inline void ws_release(bb25_index *idx, cudaStream_t st) {
     cudaEventRecord(idx->ws_ev, st);
 }
 int ensure_workspace(bb25_index *idx, size_t bytes);
+int prep_queries_launch(const bb25_index *idx, const int32_t *q_terms, const int64_t *q_off, int64_t n_q,
+                        int64_t term_base, int64_t n_terms_total, int32_t *qt_ws, uint8_t *nocount, int64_t *qo_ws,
+                        longlong2 *qt_info, int *err, cudaStream_t st);
 int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out);
 }  // namespace bb25

@@ -319,6 +319,18 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
     }
 }
 
+// The same preparation for other translation units (bb25_fused.cu): sanitised term copy,
+// duplicate flags, rebased offsets and the per-term (indptr, dense slot, table row) records of one index.
+int prep_queries_launch(const bb25_index *idx, const int32_t *q_terms, const int64_t *q_off, int64_t n_q,
+                        int64_t term_base, int64_t n_terms_total, int32_t *qt_ws, uint8_t *nocount, int64_t *qo_ws,
+                        longlong2 *qt_info, int *err, cudaStream_t st) {
+    prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(
+        q_terms, q_off, n_q, term_base, n_terms_total, idx->n_vocab, nullptr, qt_ws, nocount, qo_ws, nullptr, nullptr,
+        nullptr, err, idx->indptr, idx->dense_vals ? idx->dense_slot : nullptr, idx->tab_row, qt_info);
+    BB25_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------
 // per-query selection: sort the candidate keys (descending), then either tighten the
 // threshold (overflow / intermediate group) or write the final top-k.

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, fused
 from .fusion import _check_weights, _resolve_alpha
 
 
@@ -56,3 +56,25 @@ def hybrid_retrieve(scorer, term_ids, cosine: torch.Tensor, k: int = 100, weight
     """Top-k documents by fused probability: (ids int64 [k], fused fp64 [k]) NumPy arrays."""
     ids, vals = topk_device(hybrid_probabilities_device(scorer, term_ids, cosine, weights, alpha), k)
     return ids.cpu().numpy() + scorer._doc_id_offset, vals.cpu().numpy()
+
+
+def hybrid_retrieve_batch_device(scorer, q_terms, q_off, cosine: torch.Tensor, k: int = 100, weights=(0.6, 0.4),
+                                 alpha=None):
+    """A batch of hybrid queries: q_terms / q_off (flat in-vocabulary ids + offsets, NumPy), cosine fp32
+    CUDA [Q, N] (or [Q, stride], see fused.pad_cosine).  Returns CUDA (ids int64 [Q,k], fused fp64 [Q,k]),
+    row q equal to hybrid_retrieve(scorer, query q, cosine[q], k, weights, alpha)."""
+    scorer._require_index("hybrid_retrieve_batch()")
+    if cosine.shape[1] < scorer.num_docs:
+        raise ValueError(f"cosine must have at least {scorer.num_docs} columns, got {cosine.shape[1]}")
+    cosine = fused.pad_cosine(cosine.to(device=scorer._device, dtype=torch.float32))
+    if weights is not None:
+        w = _check_weights(weights, 2)
+        scale = float(2 ** _resolve_alpha(alpha, default=0.0))
+        return fused.retrieve_fused_batch_device([scorer], [(q_terms, q_off)], k, scale, [float(w[0])], cosine, float(w[1]))
+    scale = float(2 ** _resolve_alpha(alpha, default=0.5))
+    return fused.retrieve_fused_batch_device([scorer], [(q_terms, q_off)], k, scale, None, cosine, 1.0)
+
+
+def hybrid_retrieve_batch(scorer, q_terms, q_off, cosine: torch.Tensor, k: int = 100, weights=(0.6, 0.4), alpha=None):
+    ids, probs = hybrid_retrieve_batch_device(scorer, q_terms, q_off, cosine, k, weights, alpha)
+    return ids.cpu().numpy(), probs.cpu().numpy()

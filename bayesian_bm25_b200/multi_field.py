@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, fused
 from .fusion import _resolve_alpha
 from .scorer import BayesianBM25Scorer
 
@@ -92,12 +92,19 @@ class MultiFieldScorer:
             self._scorers[f].add_documents([doc[f] for doc in new_documents], show_progress=show_progress)
         self._num_docs += len(new_documents)
 
+    def _check_weights(self) -> None:
+        # the reference passes the weights to log_odds_conjunction at query time, which rejects
+        # negative ones (fusion.py:253-255)
+        if any(w < 0 for w in self._field_weights.values()):
+            raise ValueError("weights must be non-negative")
+
     def _fused_device(self, per_field_terms) -> torch.Tensor:
         """Fused probability of every document, on the device.  One pass per field: the
         field's traversal kernel turns its BM25 accumulators into the posterior, takes
         the logit and adds w_f * logit into ONE shared accumulator; the last field
         applies n**alpha and the sigmoid (multi_field.py:158-174 without the [N, F]
         matrix)."""
+        self._check_weights()
         nf = len(self._fields)
         first = self._scorers[self._fields[0]]
         acc = torch.empty(self._num_docs, dtype=torch.float64, device=first._device)
@@ -139,3 +146,37 @@ class MultiFieldScorer:
         """Extension: query given as one term-id list per field."""
         ids, vals = self._topk_device(self._fused_device(per_field_terms), k)
         return ids.cpu().numpy(), vals.cpu().numpy()
+
+    # ---- batched retrieval (extension): the per-query loop of the reference's consumers, absorbed ----
+    def retrieve_ids_batch_device(self, field_queries, k: int = 10):
+        """field_queries: per field, in `fields` order, (flat term ids int32, offsets int64[Q+1]).
+        Returns CUDA tensors (ids int64 [Q,k], fused fp64 [Q,k]); top-k by fused probability with
+        block-max pruning on the fused key (bb25_retrieve_fused_batch)."""
+        if not self._scorers:
+            raise RuntimeError("Call index() before retrieve_batch().")
+        self._check_weights()
+        nf = len(self._fields)
+        scale = float(nf ** _resolve_alpha(self._alpha, default=0.5))
+        weights = [self._field_weights[f] for f in self._fields]
+        return fused.retrieve_fused_batch_device([self._scorers[f] for f in self._fields], field_queries, k, scale, weights)
+
+    def retrieve_ids_batch(self, field_queries, k: int = 10):
+        ids, probs = self.retrieve_ids_batch_device(field_queries, k)
+        return ids.cpu().numpy(), probs.cpu().numpy()
+
+    def retrieve_batch(self, queries: list[list[str]], k: int = 10):
+        """Top-k by fused probability for a batch of token-list queries:
+        (doc_ids [Q,k] int64, fused probabilities [Q,k] float64); row q equals retrieve(queries[q], k)."""
+        if not self._scorers:
+            raise RuntimeError("Call index() before retrieve_batch().")
+        fq = [self._scorers[f]._term_ids_batch(queries) for f in self._fields]
+        return self.retrieve_ids_batch(fq, k)
+
+    def stats(self) -> dict:
+        """Counters of the last retrieve_batch (units visited / skipped by the block bound, candidates,
+        queries that took the dense guaranteed path, host synchronisations)."""
+        return fused.fused_stats(self._scorers[self._fields[0]])
+
+    def set_pruning(self, level: int) -> None:
+        """0: exhaustive traversal; >= 1: block-max pruning on the fused key.  Results are identical."""
+        self._scorers[self._fields[0]].set_pruning(level)

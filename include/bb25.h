@@ -275,6 +275,50 @@ int bb25_fuse_cosine_signal(int device, const float *cosine /*dev*/, int64_t n, 
 int bb25_fuse_prob_signal(int device, const double *probs /*dev*/, int64_t n, double weight, int n_signals,
                           double scale, int flags, double *acc, void *stream);
 
+/* ---- a15 + configs 4/5: batched top-k by FUSED probability ------------------------- */
+
+/* One BM25 field (= one index handle) of a fused query batch.  The queries of the batch are given
+ * per field because every field has its own vocabulary (multi_field.py:105-139). */
+typedef struct bb25_fused_field {
+    bb25_index *index;
+    bb25_params params;      /* the field's transform (alpha must be > 0) */
+    double weight;           /* conjunction weight of the field; ignored when `weighted` is 0 */
+    const int32_t *q_terms;  /* dev: in-vocabulary term ids of the field, all queries back to back */
+    const int64_t *q_off;    /* dev [Q+1] */
+    int64_t term_base;       /* host copies of q_off[0] and q_off[Q] - q_off[0] */
+    int64_t n_terms_total;
+} bb25_fused_field;
+
+/*
+ * MultiFieldScorer.retrieve (multi_field.py:176-200) and the hybrid BM25 + vector pattern
+ * (benchmarks/hybrid_beir.py:1708-1765, README.md:129-140) for a BATCH of queries: top-k documents by
+ *     fused = log_odds_conjunction([p_field_0, ..., p_field_F-1 (, cosine_to_probability(cos))], alpha, weights)
+ * (fusion.py:172-280, gating "none"), ranked (fused desc, doc id asc).  p_field_i is the field's
+ * posterior (scorer.py:564-590), 0.0 where the field's BM25 score is <= 0.
+ *   n_fields 1..4; all fields index the same documents.
+ *   cosine: dev fp32 [Q][cos_stride] or NULL; rows 16-byte aligned, cos_stride % 4 == 0, >= n_docs.
+ *           The dense signal is the LAST signal of the conjunction.
+ *   weighted != 0: weights (fields[i].weight..., cos_weight), validated by the caller as fusion.py:253-258;
+ *   weighted == 0: unweighted mean branch (fusion.py:270-279).
+ *   scale = n_signals ** alpha, alpha resolved by the caller (fusion.py:106-116).
+ *   out_ids int64 [Q][k], out_probs fp64 [Q][k] (dev).  1 <= k <= min(n_docs, 1024).
+ * The traversal prunes (block, query) units with the per-(term, block) maxima pushed through each
+ * field's probability bound and the monotone conjunction (BlockMaxIndex.bayesian_block_upper_bound,
+ * scorer.py:101-130; wand_upper_bound, probability.py:205-236) unless the first field's index is at
+ * pruning level 0; every candidate is evaluated exactly before it is ranked, so results do not depend
+ * on the level.  One stream synchronisation per batch (more only when queries take the dense path).
+ */
+int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, const float *cosine, int64_t cos_stride,
+                              double cos_weight, int weighted, double scale, int64_t n_queries, int k,
+                              int64_t *out_ids, double *out_probs, void *stream);
+/* statistics of the last bb25_retrieve_fused_batch whose first field was `idx`: (block, query) units
+ * handed out, skipped by the block-max bound, abandoned between fields (no document's running bound could
+ * still reach the threshold), candidates evaluated exactly, queries on the dense guaranteed path,
+ * re-run (query, group) pairs, host synchronisations, summed traversal-kernel time (CUDA events) */
+int bb25_fused_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped, int64_t *units_abandoned,
+                     int64_t *candidates, int64_t *fallback_queries, int64_t *rerun_queries, int64_t *host_syncs,
+                     double *traverse_ms);
+
 /* ---- a12: BlockMaxIndex ---------------------------------------------------- */
 
 /* BlockMaxIndex.build (scorer.py:55-81) on a dense [n_terms][n_docs] fp64
