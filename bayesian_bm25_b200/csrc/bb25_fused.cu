@@ -191,34 +191,16 @@ __device__ __forceinline__ float fold_pass(const FusedBlockArgs &a, const FField
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *dbase = ff.dense_vals + doc_base + lane * 4;
     float lane_max = 0.f;
-    // row pointers of the first two D terms are formed once (the address arithmetic is per row, not per chunk)
-    const int n_d = __popc(dmask);
-    const float4 *rp0 = nullptr, *rp1 = nullptr;
-    unsigned drest = 0u;
-    if (n_d >= 1)
-        rp0 = reinterpret_cast<const float4 *>(dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(dmask) - 1) * (size_t)ff.dense_stride);
-    if (n_d >= 2) {
-        const unsigned d2 = dmask & (dmask - 1);
-        rp1 = reinterpret_cast<const float4 *>(dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(d2) - 1) * (size_t)ff.dense_stride);
-        drest = d2 & (d2 - 1);
-    }
 #pragma unroll 1
     for (int h = 0; h < kBlockDocs / 256; h++) {
-        float4 v[2], ra[2], rb[2];
+        float4 v[2];
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const int w = h * 64 + j * 32 + lane;
             v[j] = has_s ? B4[w] : zero4;
-            if (n_d >= 1) ra[j] = ld_row_f4(rp0 + h * 64 + j * 32);
-            if (n_d >= 2) rb[j] = ld_row_f4(rp1 + h * 64 + j * 32);
             if (has_s) B4[w] = zero4;
         }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            if (n_d >= 1) add_f4(v[j], ra[j]);
-            if (n_d >= 2) add_f4(v[j], rb[j]);
-        }
-        for (unsigned mm = drest; mm; mm &= mm - 1) {  // third and later D terms
+        for (unsigned mm = dmask; mm; mm &= mm - 1) {
             const int slot = __shfl_sync(0xFFFFFFFFu, dslot, __ffs(mm) - 1);
             const float4 *rp = reinterpret_cast<const float4 *>(dbase + (size_t)slot * (size_t)ff.dense_stride);
             float4 r[2];
