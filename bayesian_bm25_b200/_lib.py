@@ -67,7 +67,12 @@ SIGNATURES = {
     "bb25_retrieve_batch_host": (_i32, [_vp, _PP, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "bb25_retrieve_one_dense": (_i32, [_vp, _PP, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bb25_retrieve_sync_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
-    "bb25_index_set_threshold_exchange": (_i32, [_vp, _vp, _vp]),
+    "bb25_index_set_threshold_exchange": (_i32, [_vp, _vp, _vp, _i32]),
+    "bb25_quantile_ranks": (None, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "bb25_apply_quantiles": (_i32, [_i32, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "bb25_merge_topk_peers": (_i32, [_i32, _vp, _vp, _i32, _i64, _i64, _i32, _vp]),
+    "bb25_unpack_topk": (_i32, [_i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "bb25_memcpy_device": (_i32, [_i32, _vp, _vp, _i64, _vp]),
     "bb25_retrieve_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_index_set_pruning": (_i32, [_vp, _i32]),
     "bb25_retrieve_prune_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

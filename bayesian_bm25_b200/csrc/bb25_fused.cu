@@ -45,6 +45,10 @@ constexpr int kFusedMaxK = 1024;
 constexpr int kFusedRowCap = 28672;  // candidate row per query, consumed in chunks of (sort slots - k)
 constexpr int kFusedSortCap = 8192;
 constexpr int kSeedMax = 512;
+#ifndef BB25_PRED_MAX
+#define BB25_PRED_MAX 96
+#endif
+constexpr int kPredMaxPostings = BB25_PRED_MAX;  // frequent-term restriction only for units with at most this many S postings
 constexpr int FQC = 8;     // queries per warp work item
 constexpr int FWARPS = 8;  // warps per CTA
 constexpr double kNeg = 23.02585092984;  // -logit(1e-10), probability.py:20,44-48
@@ -100,8 +104,10 @@ struct FusedBlockArgs {
     const unsigned int *n_q_ptr;
     int blk_begin, blk_end;
     int prune;
+    int pair_mode;  // two fields: both in one pass (A/B accumulators) instead of one fold pass per field
     unsigned long long *work_counter;
-    unsigned long long *stats;  // [0] units handed out, [1] skipped by the block bound, [2] abandoned between fields
+    unsigned long long *stats;  // [0] units handed out, [1] skipped by the block bound, [2] abandoned between fields,
+                                // [3] evaluated under the frequent-term restriction
 };
 
 struct FTermEnt {
@@ -277,6 +283,94 @@ __device__ __forceinline__ float fold_pass(const FusedBlockArgs &a, const FField
     return lane_max;
 }
 
+// Two fields in ONE pass (the MultiFieldScorer title + body shape): field 0's S-term sums sit in accumulator A,
+// field 1's in B; per quad both are read, the D rows of both fields are added in registers, the two bounds
+// are formed and summed, tested, emitted.  Half the shared-memory traffic of two fold passes, no running
+// bound to store -- and the frequent-term restriction of block_kernel's level 2 carries over: when the D terms
+// alone (summed block maxima, both fields) cannot reach the threshold, a quad without any S contribution
+// cannot qualify and is skipped before its rows are loaded (PRED).
+template <bool HAS_COS, bool PRED>
+__device__ __forceinline__ void pair_pass(const FusedBlockArgs &a, float4 *A4, float4 *B4, bool has_s0, bool has_s1,
+                                          unsigned dmask0, unsigned dmask1, int dslot0, int dslot1, float o0, float o1,
+                                          int doc_base, int lane, float thr, int q, const uint4 *sfd_q) {
+    const FField &f0 = a.f[0];
+    const FField &f1 = a.f[1];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *dbase0 = f0.dense_vals + doc_base + lane * 4;
+    const float *dbase1 = f1.dense_vals + doc_base + lane * 4;
+    const float ka0 = f0.ka, ka1 = f1.ka;
+#pragma unroll 1
+    for (int h = 0; h < kBlockDocs / 256; h++) {
+        float4 va[2], vb[2];
+        bool live[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int w = h * 64 + j * 32 + lane;
+            va[j] = has_s0 ? A4[w] : zero4;
+            vb[j] = has_s1 ? B4[w] : zero4;
+            live[j] = true;
+            if (PRED) {
+                const float ma = fmaxf(fmaxf(va[j].x, va[j].y), fmaxf(va[j].z, va[j].w));
+                const float mb = fmaxf(fmaxf(vb[j].x, vb[j].y), fmaxf(vb[j].z, vb[j].w));
+                live[j] = fmaxf(ma, mb) > 0.f;
+            }
+            if (live[j]) {  // an untouched quad holds zeros already
+                if (has_s0) A4[w] = zero4;
+                if (has_s1) B4[w] = zero4;
+            }
+        }
+        for (unsigned mm = dmask0; mm; mm &= mm - 1) {
+            const int slot = __shfl_sync(0xFFFFFFFFu, dslot0, __ffs(mm) - 1);
+            const float4 *rp = reinterpret_cast<const float4 *>(dbase0 + (size_t)slot * (size_t)f0.dense_stride);
+            float4 r[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) r[j] = live[j] ? ld_row_f4(rp + h * 64 + j * 32) : zero4;
+#pragma unroll
+            for (int j = 0; j < 2; j++) add_f4(va[j], r[j]);
+        }
+        for (unsigned mm = dmask1; mm; mm &= mm - 1) {
+            const int slot = __shfl_sync(0xFFFFFFFFu, dslot1, __ffs(mm) - 1);
+            const float4 *rp = reinterpret_cast<const float4 *>(dbase1 + (size_t)slot * (size_t)f1.dense_stride);
+            float4 r[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) r[j] = live[j] ? ld_row_f4(rp + h * 64 + j * 32) : zero4;
+#pragma unroll
+            for (int j = 0; j < 2; j++) add_f4(vb[j], r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (PRED && !live[j]) continue;
+            const float sa[4] = {va[j].x, va[j].y, va[j].z, va[j].w};
+            const float sb[4] = {vb[j].x, vb[j].y, vb[j].z, vb[j].w};
+            float un[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float ua = sa[c] > 0.f ? __fmaf_rn(ka0, sa[c], o0) : 0.f;
+                const float ub = sb[c] > 0.f ? __fmaf_rn(ka1, sb[c], o1) : 0.f;
+                un[c] = __fadd_rn(ua, ub);
+            }
+            const uint32_t first_id = (uint32_t)(doc_base + (h * 64 + j * 32 + lane) * 4);
+            float4 u = make_float4(un[0], un[1], un[2], un[3]);
+            if (HAS_COS) {
+                if ((int64_t)first_id < a.c.n_docs) {
+                    const float4 c4 = ld_nc_f4(reinterpret_cast<const float4 *>(a.c.cosine + (size_t)q * (size_t)a.c.cos_stride + first_id));
+                    u.x = __fadd_rn(u.x, cos_bound(c4.x, a.c.kc));
+                    u.y = __fadd_rn(u.y, cos_bound(c4.y, a.c.kc));
+                    u.z = __fadd_rn(u.z, cos_bound(c4.z, a.c.kc));
+                    u.w = __fadd_rn(u.w, cos_bound(c4.w, a.c.kc));
+                }
+            }
+            const float mx = fmaxf(fmaxf(u.x, u.y), fmaxf(u.z, u.w));
+            if (mx > 0.f && mx >= thr) {
+                uint32_t m4 = 0u;
+#pragma unroll
+                for (int c = 0; c < 4; c++) m4 |= ((sa[c] > 0.f ? 1u : 0u) | (sb[c] > 0.f ? 2u : 0u)) << (8 * c);
+                emit_quad_fused(a, u, m4, first_id, thr, q, sfd_q);
+            }
+        }
+    }
+}
+
 // A unit in which no field has a posting still holds 1024 documents with a dense-signal value each.
 template <bool HAS_COS>
 __device__ __forceinline__ void cos_only_pass(const FusedBlockArgs &a, int doc_base, int lane, float thr, int q,
@@ -301,7 +395,7 @@ __device__ __forceinline__ void cos_only_pass(const FusedBlockArgs &a, int doc_b
 // the unit is abandoned when no document's running bound plus the remaining fields' block bounds can reach
 // the threshold -- the per-document version of the block-max test, far tighter because it uses the scores
 // the documents of the block actually have in the fields seen so far instead of the sum of per-term maxima.
-template <int F, bool HAS_COS>
+template <int F, bool HAS_COS, bool PAIR>
 __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kernel(const __grid_constant__ FusedBlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int kAccBytes = (F >= 2 ? 2 : 1) * kBlockDocs * 4;
@@ -315,6 +409,8 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
     uint4 *sfd = reinterpret_cast<uint4 *>(wbase + kAccBytes);                    // [FQC][F]: t0, m, o bits, P_tf bits
     uint2 *sq = reinterpret_cast<uint2 *>(wbase + kAccBytes + FQC * F * 16);      // [FQC]: q, threshold bits
     for (int i = lane; i < kBlockDocs / 4; i += 32) B4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (PAIR)
+        for (int i = lane; i < kBlockDocs / 4; i += 32) U4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
 
     const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
@@ -322,7 +418,7 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
-    unsigned int skipped = 0u, abandoned = 0u;
+    unsigned int skipped = 0u, abandoned = 0u, restricted = 0u;
 
     for (;;) {
         long long item = 0;
@@ -392,9 +488,60 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
                 cos_only_pass<HAS_COS>(a, doc_base, lane, thr, q, sfd_q);
                 continue;
             }
+            if (PAIR) {
+                // ---- two fields, one pass ----
+                unsigned dm[2], sm[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    dm[i] = __ballot_sync(0xFFFFFFFFu, e[i].dslot >= 0);
+                    sm[i] = pres[i] & ~dm[i];
+                    float *acc = i == 0 ? reinterpret_cast<float *>(U4) : B;
+                    bool fresh = true;
+                    for (unsigned mm = sm[i]; mm; mm &= mm - 1) {
+                        const int t = __ffs(mm) - 1;
+                        const int len = __shfl_sync(0xFFFFFFFFu, e[i].len, t);
+                        const long long s = shfl_ll(e[i].start, t);
+                        if (fresh) scatter_block<true>(a.f[i].data, a.f[i].indices, s, len, acc, doc_base, lane);
+                        else scatter_block<false>(a.f[i].data, a.f[i].indices, s, len, acc, doc_base, lane);
+                        fresh = false;
+                        __syncwarp();
+                    }
+                }
+                // documents matching frequent (D) terms only: bounded by the D terms' block maxima in both fields
+                bool pred = false;
+                if (a.prune >= 2 && thr > 0.f && !HAS_COS) {
+                    float dub = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const float ds = __fmul_rn(warp_sum_f(e[i].dslot >= 0 ? e[i].bmax : 0.f), 1.000004f);
+                        if (dm[i]) dub = __fadd_rn(dub, fminf(__fmul_rn(__fmaf_rn(a.f[i].ka, ds, ofs[i]), 1.000002f), a.f[i].ucap));
+                    }
+                    pred = __fmul_rn(dub, 1.000002f) < thr;
+                    if (pred && !(sm[0] | sm[1])) {
+                        restricted++;
+                        continue;  // no S posting in the block at all: nothing here can qualify
+                    }
+                    if (pred) {
+                        // worth it only while the S postings are sparse (most quads untouched); measured: with
+                        // dense S hits the predicated row loads cost more than they save
+                        const int n_s = warp_sum((((sm[0] >> lane) & 1u) ? e[0].len : 0) + (((sm[1] >> lane) & 1u) ? e[1].len : 0));
+                        pred = n_s <= kPredMaxPostings;
+                    }
+                    if (pred) restricted++;
+                }
+                float4 *A4 = reinterpret_cast<float4 *>(U4);
+                if (pred)
+                    pair_pass<HAS_COS, true>(a, A4, B4, sm[0] != 0u, sm[1] != 0u, dm[0], dm[1], e[0].dslot, e[1].dslot, ofs[0], ofs[1],
+                                             doc_base, lane, thr, q, sfd_q);
+                else
+                    pair_pass<HAS_COS, false>(a, A4, B4, sm[0] != 0u, sm[1] != 0u, dm[0], dm[1], e[0].dslot, e[1].dslot, ofs[0], ofs[1],
+                                              doc_base, lane, thr, q, sfd_q);
+                __syncwarp();
+                continue;
+            }
             bool started = false;
 #pragma unroll
-            for (int i = 0; i < F; i++) {
+            for (int i = 0; i < (PAIR ? 0 : F); i++) {
                 if (!pres[i]) continue;
                 const FField &ff = a.f[i];
                 const unsigned dmask = __ballot_sync(0xFFFFFFFFu, e[i].dslot >= 0);
@@ -430,6 +577,7 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
     if (lane == 0) {
         if (skipped) atomicAdd(&a.stats[1], (unsigned long long)skipped);
         if (abandoned) atomicAdd(&a.stats[2], (unsigned long long)abandoned);
+        if (restricted) atomicAdd(&a.stats[3], (unsigned long long)restricted);
     }
 }
 
@@ -823,7 +971,7 @@ __global__ void fused_mark_bad_kernel(const int32_t *__restrict__ list, const un
 }
 
 struct FusedReport {
-    unsigned long long n_cand, units, skipped, abandoned;
+    unsigned long long n_cand, units, skipped, abandoned, restricted;
     unsigned int n_fallback, reruns;
     int err;
     int pad;
@@ -844,6 +992,7 @@ __global__ void fused_report_kernel(const uint8_t *__restrict__ flags, int64_t n
         r.units = stats[0];
         r.skipped = stats[1];
         r.abandoned = stats[2];
+        r.restricted = stats[3];
         r.n_fallback = s_n;
         unsigned int re = 0;
         for (int i = 0; i < n_round_cnt; i++) re += round_cnt[i];
@@ -858,12 +1007,12 @@ __global__ void add_offset_kernel(int64_t *ids, int n, int64_t off) {
     if (i < n) ids[i] += off;
 }
 
-template <int F, bool HAS_COS>
+template <int F, bool HAS_COS, bool PAIR>
 static int launch_fused_block_inst(const bb25_index *idx, const FusedBlockArgs &a, cudaStream_t st) {
     constexpr int kAccBytes = (F >= 2 ? 2 : 1) * kBlockDocs * 4;
     constexpr int kWarpBytes = kAccBytes + FQC * 8 + FQC * F * 16;
     const size_t smem = (size_t)FWARPS * kWarpBytes;
-    BB25_CUDA(cudaFuncSetAttribute(fused_block_kernel<F, HAS_COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BB25_CUDA(cudaFuncSetAttribute(fused_block_kernel<F, HAS_COS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_chunks = (a.n_q + FQC - 1) / FQC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (n_items <= 0) return 0;
@@ -871,17 +1020,19 @@ static int launch_fused_block_inst(const bb25_index *idx, const FusedBlockArgs &
     const long long need = (n_items + FWARPS - 1) / FWARPS;
     if (grid > need) grid = need;
     BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-    fused_block_kernel<F, HAS_COS><<<(unsigned)grid, FWARPS * 32, smem, st>>>(a);
+    fused_block_kernel<F, HAS_COS, PAIR><<<(unsigned)grid, FWARPS * 32, smem, st>>>(a);
     BB25_LAUNCH_CHECK();
     return 0;
 }
 static int launch_fused_block(const bb25_index *idx, const FusedBlockArgs &a, cudaStream_t st) {
     const bool hc = a.c.has_cos != 0;
     switch (a.c.n_fields) {
-    case 1: return hc ? launch_fused_block_inst<1, true>(idx, a, st) : launch_fused_block_inst<1, false>(idx, a, st);
-    case 2: return hc ? launch_fused_block_inst<2, true>(idx, a, st) : launch_fused_block_inst<2, false>(idx, a, st);
-    case 3: return hc ? launch_fused_block_inst<3, true>(idx, a, st) : launch_fused_block_inst<3, false>(idx, a, st);
-    case 4: return hc ? launch_fused_block_inst<4, true>(idx, a, st) : launch_fused_block_inst<4, false>(idx, a, st);
+    case 1: return hc ? launch_fused_block_inst<1, true, false>(idx, a, st) : launch_fused_block_inst<1, false, false>(idx, a, st);
+    case 2:
+        if (a.pair_mode) return hc ? launch_fused_block_inst<2, true, true>(idx, a, st) : launch_fused_block_inst<2, false, true>(idx, a, st);
+        return hc ? launch_fused_block_inst<2, true, false>(idx, a, st) : launch_fused_block_inst<2, false, false>(idx, a, st);
+    case 3: return hc ? launch_fused_block_inst<3, true, false>(idx, a, st) : launch_fused_block_inst<3, false, false>(idx, a, st);
+    case 4: return hc ? launch_fused_block_inst<4, true, false>(idx, a, st) : launch_fused_block_inst<4, false, false>(idx, a, st);
     default: set_error("unsupported number of fields %d", a.c.n_fields); return 1;
     }
 }
@@ -1109,7 +1260,9 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
             });
             for (int i = 0; i < n_fields; i++) ba.f[i] = ff[order[i]];
         }
-        ba.prune = idx0->prune > 0 ? 1 : 0;
+        ba.prune = idx0->prune;
+        ba.pair_mode = n_fields == 2 ? 1 : 0;
+        if (const char *e = getenv("BB25_FUSED_PAIR")) ba.pair_mode = (n_fields == 2 && atoi(e) != 0) ? 1 : 0;
         ba.work_counter = d_work;
         ba.stats = d_stats;
         float trav_ms = 0.f;
@@ -1162,7 +1315,7 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         }
         idx0->fz_units = (int64_t)h_rep->units;
         idx0->fz_skipped = (int64_t)h_rep->skipped;
-        idx0->fz_abandoned = (int64_t)h_rep->abandoned;
+        idx0->fz_abandoned = (int64_t)h_rep->abandoned + (int64_t)h_rep->restricted;
         idx0->fz_candidates = (int64_t)h_rep->n_cand;
         idx0->fz_fallback = (int64_t)h_rep->n_fallback;
         idx0->fz_reruns = (int64_t)h_rep->reruns;

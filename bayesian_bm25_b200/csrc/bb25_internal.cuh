@@ -279,6 +279,7 @@ struct bb25_index {
     // sharded retrieval: called between block groups so that the ranks can agree on tighter thresholds
     bb25_exchange_fn exchange_cb = nullptr;
     void *exchange_user = nullptr;
+    int exchange_shards = 0;
 };
 
 namespace bb25 {

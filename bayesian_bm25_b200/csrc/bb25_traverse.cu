@@ -337,6 +337,10 @@ int prep_queries_launch(const bb25_index *idx, const int32_t *q_terms, const int
 // ---------------------------------------------------------------------------------
 struct SelectArgs {
     const int32_t *q_list;
+    // sharded retrieval: scores at a few ranks of the running top-k, published between block groups
+    unsigned long long *quant;  // [n_q][n_quant] or NULL; entry n_quant-1 (rank k = the threshold) is filled separately
+    int n_quant;
+    int qrank[4];
     int n_list;                      // number of queries to process (host-side count) ...
     const unsigned int *n_list_ptr;  // ... or, when set, read on the device
     unsigned int *cand_cnt;
@@ -655,6 +659,8 @@ __device__ __forceinline__ void select_one(const SelectArgs &a, unsigned char *s
         // keep the best k (order irrelevant), raise the threshold to the k-th key
         if (sorted) {
             for (int i = tid; i < k; i += NT) row[i] = top[i];
+            // "this shard holds qrank[j] documents with at least this score" (score bits only: doc ids are shard-local)
+            if (a.quant && tid < a.n_quant - 1) a.quant[(size_t)q * a.n_quant + tid] = top[a.qrank[tid] - 1] & ~((1ull << 33) - 1ull);
         } else {
             if (tid == 0) st[2] = 0u;
             __syncthreads();
@@ -1802,6 +1808,12 @@ __global__ void report_kernel(const unsigned long long *__restrict__ n_cand, con
     *out = r;
 }
 __global__ void copy_u32_kernel(const unsigned int *src, unsigned int *dst) { *dst = *src; }
+// rank-k entry of the published quantiles = the shard's current threshold (score bits)
+__global__ void publish_thr_kernel(const unsigned long long *__restrict__ thr, int64_t n_q, int J,
+                                   unsigned long long *__restrict__ quant) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_q) quant[q * J + (J - 1)] = thr[q] & ~((1ull << 33) - 1ull);
+}
 
 constexpr int kMaxRepairRounds = 6;
 
@@ -1845,7 +1857,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     const long long route_max = (long long)idx->n_docs / route_div;
     const bool use_cand = use_block_kernel() && idx->prune >= 3 && idx->dense_slot != nullptr && n_q > 0;
     const size_t items_cap = use_cand ? (size_t)n_q * (size_t)(route_max / kCandChunk + 25) : 1;
-    const size_t o_info = align_up(o_badlist + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_quant = align_up(o_badlist + sizeof(int32_t) * (size_t)n_q);
+    const size_t o_info = align_up(o_quant + sizeof(unsigned long long) * 4 * (size_t)n_q);
     const size_t o_items = align_up(o_info + 2 * sizeof(longlong2) * nt);
     const size_t o_key = align_up(o_items + sizeof(uint2) * items_cap);
     const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
@@ -1870,6 +1883,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     BatchReport *d_report = (BatchReport *)(ws + o_ctr + 512);
     uint8_t *d_bad = ws + o_bad;
     int32_t *d_badlist = (int32_t *)(ws + o_badlist);
+    unsigned long long *d_quant = (unsigned long long *)(ws + o_quant);
+    int n_quant = 0, qranks[4] = {k, k, k, k};
+    if (idx->exchange_cb) bb25_quantile_ranks(k, idx->exchange_shards, &n_quant, qranks);
     unsigned long long *d_keys = (unsigned long long *)(ws + o_key);
 
     const float *kth = nullptr;
@@ -1981,6 +1997,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     sa.q_nocount = d_nc;
     sa.q_off = d_qo;
     sa.term_base = 0;
+    sa.quant = idx->exchange_cb ? d_quant : nullptr;
+    sa.n_quant = n_quant;
+    for (int j = 0; j < 4; j++) sa.qrank[j] = qranks[j];
 
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
@@ -2095,6 +2114,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     // ---- block / tile traversal of the remaining queries, group by group -----------
     for (int gi = 0; gi < ng; gi++) {
         unsigned int *rc = d_round + (size_t)(gi + 1) * kRoundStride;
+        if (idx->exchange_cb && gi + 1 < ng)
+            BB25_CUDA(cudaMemsetAsync(d_quant, 0, sizeof(unsigned long long) * (size_t)n_quant * (size_t)n_q, st));
         for (int r = 0; r <= n_rounds; r++) {
             const int32_t *list = r == 0 ? blk_list : d_list[(r - 1) & 1];
             const unsigned int *n_list = r == 0 ? blk_n_ptr : rc + r;
@@ -2131,7 +2152,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         BB25_LAUNCH_CHECK();
         if (gi + 1 < ng && idx->exchange_cb) {
             // sharded retrieval: the ranks agree on tighter thresholds between block groups
-            if (idx->exchange_cb(idx->exchange_user, (void *)d_thr, (void *)d_cnt, (void *)d_keys, n_q, cap, k, gi, (void *)st)) {
+            publish_thr_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, st>>>(d_thr, n_q, n_quant, d_quant);
+            BB25_LAUNCH_CHECK();
+            if (idx->exchange_cb(idx->exchange_user, (void *)d_quant, (void *)d_thr, n_q, n_quant, k, gi, (void *)st)) {
                 set_error("threshold exchange callback failed");
                 return 1;
             }
@@ -2417,11 +2440,13 @@ int bb25_retrieve_one_dense(bb25_index *idx, const bb25_params *params, const in
     return rc;
 }
 
-int bb25_index_set_threshold_exchange(bb25_index *idx, bb25_exchange_fn fn, void *user) {
+int bb25_index_set_threshold_exchange(bb25_index *idx, bb25_exchange_fn fn, void *user, int n_shards) {
     if (!idx) { set_error("index is NULL"); return 1; }
+    if (fn && (n_shards < 2 || n_shards > 32)) { set_error("n_shards must be in [2, 32]"); return 1; }
     std::lock_guard<std::mutex> lock(idx->mu);
     idx->exchange_cb = fn;
     idx->exchange_user = user;
+    idx->exchange_shards = fn ? n_shards : 0;
     return 0;
 }
 

@@ -537,7 +537,7 @@ def main():
             "config": {
                 "workload": (f"{args.docs} docs, {VOCAB}-term Zipf vocab (avg len {AVG_LEN:g}), nnz {nnz_full}, "
                              f"{args.queries}-query batch (3-5 terms), top-{args.k}, exhaustive traversal, base_rate=auto"),
-                "parallelism": f"doc-range shards x{world}" + (f" + NCCL {args.exchange} exchange and device merge" if world > 1 else ""),
+                "parallelism": f"doc-range shards x{world}" + (f" + {retr.exchange_used}" + ("; cross-shard threshold exchange between block groups" if not args.no_thr_exchange else "") if world > 1 else ""),
                 "cache": "inputs larger than L2 (CSC index %.2f GB per GPU, 126 MB L2)" % (nnz_full * 8 / world / 1e9),
                 "probabilities": "fp64 posterior fused on device", "index_build_s": round(t_build, 1),
                 "transform": {"alpha": params3[0], "beta": params3[1], "base_rate": params3[2],

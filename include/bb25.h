@@ -160,13 +160,32 @@ int bb25_retrieve_one_dense(bb25_index *idx, const bb25_params *params, const in
 int bb25_retrieve_sync_stats(const bb25_index *idx, int64_t *host_syncs, int64_t *repaired_queries,
                              int64_t *dense_fallback_queries);
 
-/* Sharded retrieval: `fn` is called on the host between the block groups of a batch
- * (group = 0, 1, ...), after the group's work has been enqueued on `stream`, so that the ranks can
- * raise each other's thresholds (bb25_publish_quantiles / an all-gather / bb25_apply_quantiles,
- * all stream-ordered -- the callback must not synchronise).  Return non-zero to fail the batch. */
-typedef int (*bb25_exchange_fn)(void *user, void *d_thr, void *d_cand_cnt, void *d_cand_key, int64_t n_queries,
-                                int cap, int k, int group, void *stream);
-int bb25_index_set_threshold_exchange(bb25_index *idx, bb25_exchange_fn fn, void *user);
+/* Sharded retrieval, cross-shard thresholds.  When `fn` is set, the batch publishes -- per query,
+ * after every block group but the last -- the scores at a few ranks of the shard's running top-k
+ * (bb25_quantile_ranks: ceil(k/S), ceil(2k/S), ceil(4k/S), k) into d_quant [n_queries][n_levels] (uint64,
+ * fp32 score bits << 33, 0 = not known) and calls `fn` on the host, with the group's work already enqueued on
+ * `stream`.  `fn` all-gathers d_quant across the ranks and hands the result to bb25_apply_quantiles, which
+ * raises d_thr to the largest score for which the shards' published counts add up to k (a lower bound of the
+ * GLOBAL k-th score), so every shard prunes and emits against the global bound.  Everything is stream-ordered;
+ * `fn` must not synchronise.  Return non-zero to fail the batch. */
+typedef int (*bb25_exchange_fn)(void *user, void *d_quant, void *d_thr, int64_t n_queries, int n_levels, int k,
+                                int group, void *stream);
+int bb25_index_set_threshold_exchange(bb25_index *idx, bb25_exchange_fn fn, void *user, int n_shards);
+void bb25_quantile_ranks(int k, int n_shards, int *n_levels, int *ranks4);
+/* all_quantiles: dev uint64 [n_shards][n_queries][n_levels], rank-major as an all-gather leaves it */
+int bb25_apply_quantiles(int device, const void *all_quantiles, int n_shards, int64_t n_queries, int k, void *d_thr,
+                         void *stream);
+
+/* Exchange + merge in ONE kernel over peer memory (NVLink): this rank merges the queries
+ * [q_begin, q_begin + n_queries).  src_tab_dev / dst_tab_dev: DEVICE arrays of n_shards pointers (symmetric
+ * memory: entry s = rank s's buffer mapped into this process); every source buffer holds that shard's packed
+ * [Q][k][2] lists (bb25_pack_topk), every destination buffer receives the merged packed rows of these queries.
+ * The caller separates it from the producers / consumers of the buffers with device-side barriers. */
+int bb25_merge_topk_peers(int device, const void *src_tab_dev, const void *dst_tab_dev, int n_shards, int64_t q_begin,
+                          int64_t n_queries, int k, void *stream);
+int bb25_unpack_topk(int device, const int64_t *packed /*dev [n][2]*/, int64_t n, int64_t *out_ids, float *out_scores,
+                     double *out_probs, void *stream);
+int bb25_memcpy_device(int device, void *dst, const void *src, int64_t bytes, void *stream);
 
 /* statistics of the last bb25_retrieve_batch on this handle: kernel launches,
  * traversal passes (1 per tile group + re-runs), re-run (query,group) units,

@@ -43,6 +43,43 @@ def _worker(rank, world, port, out_dir):
     full = {k_: (v.numpy() if isinstance(v, torch.Tensor) else v) for k_, v in csc.items()}
     f_ids, f_sc, f_pr, _ = coracle.retrieve_batch(full, params, q_terms, q_off, k, n_threads=1)
     ok = np.array_equal(m_ids, f_ids) and np.array_equal(m_sc, f_sc) and np.allclose(m_pr, f_pr, rtol=0, atol=1e-15)
+
+    # the query-sliced exchange (all_to_all of query slices, merge of the own slice, all_gather of the merged
+    # slices): the host logic of ShardedRetriever._exchange_sliced with the device kernels played by NumPy / the oracle
+    def pack(i_, s_, p_, out=None):
+        key = (s_.numpy().view(np.uint32).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - i_.numpy().astype(np.uint64))
+        t = torch.from_numpy(np.stack([key.view(np.int64), p_.numpy().view(np.int64)], axis=-1))
+        if out is not None:
+            out.copy_(t)
+            return out
+        return t
+
+    def unpack(pk):
+        a = pk.numpy()
+        key = a[..., 0].view(np.uint64)
+        ids_ = (np.uint64(0xFFFFFFFF) - (key & np.uint64(0xFFFFFFFF))).astype(np.int64)
+        sc_ = (key >> np.uint64(32)).astype(np.uint32).view(np.float32)
+        return torch.from_numpy(ids_), torch.from_numpy(sc_.copy()), torch.from_numpy(a[..., 1].view(np.float64).copy())
+
+    def merge_packed(pk):
+        parts = [unpack(pk[s_]) for s_ in range(pk.shape[0])]
+        m = coracle.merge_topk(np.stack([p[0].numpy() for p in parts]), np.stack([p[1].numpy() for p in parts]),
+                               np.stack([p[2].numpy() for p in parts]))
+        return tuple(torch.from_numpy(x) for x in m)
+
+    sharded.pack_topk_device, sharded.unpack_topk_device, sharded.merge_packed_device = pack, unpack, merge_packed
+
+    class _Scorer:  # the retriever only needs these attributes for the exchange
+        _handle = None
+        _device = torch.device("cpu")
+
+    retr = sharded.ShardedRetriever(_Scorer(), exchange="sliced", threshold_exchange=False)
+    for nq in (12, 11, 1):  # 11 and 1 exercise the padding of the query slices
+        s_ids, s_sc, s_pr = retr._exchange_sliced(torch.from_numpy(ids[:nq].copy()), torch.from_numpy(sc[:nq].copy()),
+                                                  torch.from_numpy(pr[:nq].copy()))
+        ok = ok and np.array_equal(s_ids.numpy(), f_ids[:nq]) and np.array_equal(s_sc.numpy(), f_sc[:nq]) \
+            and np.allclose(s_pr.numpy(), f_pr[:nq], rtol=0, atol=1e-15)
+    ok = ok and retr.exchange_used.startswith("sliced: all_to_all_single")
     with open(os.path.join(out_dir, f"rank{rank}.ok"), "w") as f:
         f.write("1" if ok else "0")
     dist.barrier()
