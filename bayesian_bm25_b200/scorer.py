@@ -437,9 +437,7 @@ class BayesianBM25Scorer:
         if self._transform is None:
             raise RuntimeError("Call index() before retrieve().")
         if explain:
-            raise NotImplementedError(
-                "explain=True builds FusionDebugger traces (bayesian_bm25/debug.py), which is outside "
-                "the B200 hot path; run the reference's debugger on the returned ids")
+            return self._retrieve_explained(query_tokens, k)
         nq = len(query_tokens)
         if nq < 2 * PIPELINE_MIN_CHUNK or k > MAX_DEVICE_K or k > self._num_docs:
             flat, off = self._term_ids_batch(query_tokens)
@@ -460,6 +458,50 @@ class BayesianBM25Scorer:
                 pending = pool.submit(self._host_call, *staged, k, h_ids[s:e], None, h_pr[s:e])
             pending.result()
         return h_ids.numpy(), h_pr.numpy()
+
+    def _retrieve_explained(self, query_tokens, k: int) -> "RetrievalResult":
+        """retrieve(explain=True) (scorer.py:538-562): per returned document the BM25SignalTrace of
+        FusionDebugger.trace_bm25 (debug.py:178-216) -- tf and every intermediate of the posterior computed on
+        the device for the (Q, k) result set -- or None where the score is <= 0."""
+        from .debug import BM25SignalTrace
+        flat, off = self._term_ids_batch(query_tokens)
+        ids, scores, probs = self.retrieve_ids(flat, off, k, return_scores=True)
+        nq = len(query_tokens)
+        dev = self._device
+        d_terms = torch.from_numpy(flat if flat.size else np.zeros(1, np.int32)).to(dev)
+        d_off = torch.from_numpy(off).to(dev)
+        d_ids = torch.from_numpy(np.ascontiguousarray(ids)).to(dev)
+        d_tf = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        lib = _lib.lib()
+        _lib.check(lib.bb25_match_counts(self._handle, d_terms.data_ptr(), d_off.data_ptr(), nq, k, d_ids.data_ptr(),
+                                         d_tf.data_ptr(), _lib.stream_ptr()))
+        tf = d_tf.cpu().numpy().astype(np.float64)
+        ratio = self._doc_lengths[ids - self._doc_id_offset] / self._avgdl
+        d_sc = torch.from_numpy(scores.astype(np.float64)).to(dev)
+        d_tfd = torch.from_numpy(tf).to(dev)
+        d_r = torch.from_numpy(np.ascontiguousarray(ratio)).to(dev)
+        out = torch.empty((nq * k, 7), dtype=torch.float64, device=dev)
+        p = self._params()
+        _lib.check(lib.bb25_trace_bm25(dev.index, C.byref(p), d_sc.data_ptr(), d_tfd.data_ptr(), d_r.data_ptr(), nq * k,
+                                       out.data_ptr(), _lib.stream_ptr()))
+        tr = out.cpu().numpy().reshape(nq, k, 7)
+        t = self._transform
+        lbr = float(np.log(t.base_rate / (1.0 - t.base_rate))) if t.base_rate is not None else None
+        explanations = []
+        for q in range(nq):
+            row = []
+            for r in range(k):
+                if scores[q, r] > 0:
+                    v = tr[q, r]
+                    row.append(BM25SignalTrace(
+                        raw_score=float(scores[q, r]), tf=float(tf[q, r]), doc_len_ratio=float(ratio[q, r]),
+                        likelihood=float(v[0]), tf_prior=float(v[1]), norm_prior=float(v[2]), composite_prior=float(v[3]),
+                        logit_likelihood=float(v[4]), logit_prior=float(v[5]), logit_base_rate=lbr, posterior=float(v[6]),
+                        alpha=t.alpha, beta=t.beta, base_rate=t.base_rate))
+                else:
+                    row.append(None)
+            explanations.append(row)
+        return RetrievalResult(doc_ids=ids, probabilities=probs, explanations=explanations)
 
     def index_info(self) -> dict:
         """Sizes of the device index (bb25_index_info / bb25_index_table_info)."""

@@ -338,6 +338,32 @@ int bb25_fused_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipp
                      int64_t *candidates, int64_t *fallback_queries, int64_t *rerun_queries, int64_t *host_syncs,
                      double *traverse_ms);
 
+/* ---- query-time consumers of the probabilities ------------------- */
+
+/* tf of returned documents: out_tf[q*k + r] = number of DISTINCT terms of query q whose posting list holds
+ * document ids[q*k + r] (global id); scorer.py:592-601 as used by retrieve(explain=True), scorer.py:546-552.
+ * q_terms / q_off / ids / out_tf: dev. */
+int bb25_match_counts(bb25_index *idx, const int32_t *q_terms, const int64_t *q_off, int64_t n_queries, int k,
+                      const int64_t *ids, int32_t *out_tf, void *stream);
+/* FusionDebugger.trace_bm25 (debug.py:178-216) for n (score, tf, doc_len_ratio) triples: out[i*7 ..] =
+ * likelihood, tf_prior, norm_prior, composite_prior, logit(likelihood), logit(composite_prior), posterior. */
+int bb25_trace_bm25(int device, const bb25_params *p, const double *score, const double *tf, const double *ratio,
+                    int64_t n, double *out /*dev [n][7]*/, void *stream);
+/* AttentionLogOddsWeights._compute_weights (fusion.py:757-772): softmax(query_features @ W^T + b) per row.
+ * query_features [m][n_features], W [n_signals][n_features], b [n_signals], out [m][n_signals]; all dev fp64. */
+int bb25_attention_weights(int device, const double *query_features, const double *W, const double *b, int64_t m,
+                           int n_features, int n_signals, double *out, void *stream);
+/* AttentionLogOddsWeights.__call__ / compute_upper_bounds (fusion.py:774-828, 1039-1082) over m candidates:
+ * sigmoid(scale * sum_i w_i * x_i [+ logit_base_rate]), x = logit(clamp(p)), optionally min-max normalised per
+ * signal over the m candidates (normalize != 0).  weights: [1][n] (one query) or [m][n] (one row per candidate). */
+int bb25_attention_fuse(int device, const double *probs /*dev [m][n]*/, int64_t m, int n_signals, const double *weights,
+                        int64_t n_weight_rows, double scale, int has_base_rate, double logit_base_rate, int normalize,
+                        double *out /*dev [m]*/, void *stream);
+/* balanced_log_odds_fusion (fusion.py:283-333): weight * minmax(logit(cosine_to_probability(dense))) +
+ * (1 - weight) * minmax(logit(clamp(sparse))), min-max over the n candidates. */
+int bb25_balanced_fusion(int device, const double *sparse_probs, const double *dense_similarities, int64_t n, double weight,
+                         double *out, void *stream);
+
 /* ---- a12: BlockMaxIndex ---------------------------------------------------- */
 
 /* BlockMaxIndex.build (scorer.py:55-81) on a dense [n_terms][n_docs] fp64

@@ -268,8 +268,100 @@ def multifield_blockmax():
     print("multifield_blockmax ok")
 
 
+def extras():
+    """balanced_log_odds_fusion, AttentionLogOddsWeights inference
+    (__call__ / compute_upper_bounds / prune), retrieve(explain=True) traces -- outputs of the reference."""
+    from bayesian_bm25.debug import FusionDebugger
+    from bayesian_bm25.fusion import AttentionLogOddsWeights, balanced_log_odds_fusion
+    rng = np.random.default_rng(77)
+    out = {}
+    meta = {"attention": [], "explain": {}}
+    # balanced fusion
+    sp = rng.uniform(0, 1, 400)
+    sp[:5] = [0.0, 1.0, 1e-12, 0.5, 0.999999]
+    de = rng.uniform(-1, 1, 400)
+    de[:3] = [-1.0, 1.0, 0.0]
+    out["bal_sparse"], out["bal_dense"] = sp, de
+    for w in (0.5, 0.3, 0.0, 1.0):
+        out[f"bal_w{w}"] = balanced_log_odds_fusion(sp, de, weight=w)
+    out["bal_const_sparse"] = balanced_log_odds_fusion(np.full(50, 0.3), de[:50], weight=0.4)
+    out["bal_const_dense"] = balanced_log_odds_fusion(sp[:50], np.full(50, 0.2), weight=0.4)
+    # attention weights (random "trained" parameters)
+    for ci, (n_sig, n_qf, alpha, norm, br) in enumerate(((3, 4, 0.5, False, None), (2, 6, "auto", True, None),
+                                                        (4, 3, 0.0, False, 0.1), (3, 5, 1.0, True, 0.02))):
+        a = AttentionLogOddsWeights(n_sig, n_qf, alpha=alpha, normalize=norm, seed=3 + ci, base_rate=br)
+        out[f"att{ci}_W_init"] = a._W.copy()
+        a._W = rng.normal(0, 1.0, (n_sig, n_qf))
+        a._b = rng.normal(0, 0.5, n_sig)
+        a._W_avg = a._W * 0.9
+        a._b_avg = a._b * 1.1
+        m = 64
+        P = rng.uniform(0, 1, (m, n_sig))
+        P[0, :] = 0.0
+        P[1, :] = 1.0
+        qf1 = rng.normal(0, 1, n_qf)
+        qfm = rng.normal(0, 1, (m, n_qf))
+        UB = np.minimum(1.0, P + rng.uniform(0, 0.3, (m, n_sig)))
+        pre = f"att{ci}_"
+        out[pre + "W"], out[pre + "b"], out[pre + "P"], out[pre + "qf1"], out[pre + "qfm"], out[pre + "UB"] = a._W, a._b, P, qf1, qfm, UB
+        out[pre + "w1"] = a._compute_weights(qf1)
+        out[pre + "wm"] = a._compute_weights(qfm)
+        out[pre + "wm_avg"] = a._compute_weights(qfm, use_averaged=True)
+        out[pre + "call_single"] = np.array([a(P[5], qf1)])
+        out[pre + "call_batch_q1"] = a(P, qf1)
+        out[pre + "call_batch_qm"] = a(P, qfm)
+        out[pre + "call_batch_avg"] = a(P, qfm, use_averaged=True)
+        out[pre + "ub_q1"] = a.compute_upper_bounds(UB, qf1)
+        out[pre + "ub_qm"] = a.compute_upper_bounds(UB, qfm)
+        thr = float(np.median(out[pre + "ub_qm"]))
+        idx, fused = a.prune(P, qfm, thr, upper_bound_probs=UB)
+        out[pre + "prune_idx"], out[pre + "prune_fused"] = idx.astype(np.int64), fused
+        idx2, fused2 = a.prune(P, qf1, thr)
+        out[pre + "prune2_idx"], out[pre + "prune2_fused"] = idx2.astype(np.int64), fused2
+        meta["attention"].append({"n_signals": n_sig, "n_query_features": n_qf, "alpha": alpha, "normalize": norm,
+                                  "base_rate": br, "seed": 3 + ci, "threshold": thr})
+    # trace_bm25 sweep
+    s = rng.uniform(0, 25, 300)
+    tf = rng.integers(0, 13, 300).astype(np.float64)
+    r = rng.uniform(0, 3, 300)
+    out["tr_s"], out["tr_tf"], out["tr_r"] = s, tf, r
+    for ti, (a_, b_, br_) in enumerate(((1.0, 0.0, None), (2.02, 0.21, 0.045), (0.4, 6.0, 0.5))):
+        dbg = FusionDebugger(BayesianProbabilityTransform(a_, b_, base_rate=br_))
+        rows = []
+        for i in range(300):
+            t = dbg.trace_bm25(float(s[i]), float(tf[i]), float(r[i]))
+            rows.append([t.likelihood, t.tf_prior, t.norm_prior, t.composite_prior, t.logit_likelihood, t.logit_prior,
+                         t.posterior, np.nan if t.logit_base_rate is None else t.logit_base_rate])
+        out[f"tr_out{ti}"] = np.array(rows)
+    meta["trace_params"] = [[1.0, 0.0, None], [2.02, 0.21, 0.045], [0.4, 6.0, 0.5]]
+    # retrieve(explain=True) on a small corpus
+    corpus, queries = generate_synthetic_corpus(300, 200, 30, np.random.default_rng(7))
+    queries = queries[:12] + [[], ["nope"], ["term_0", "term_0", "term_3"]]
+    sc = BayesianBM25Scorer(k1=1.2, b=0.75, method="lucene", base_rate="auto")
+    sc.index(corpus, show_progress=False)
+    res = sc.retrieve(queries, k=10, explain=True)
+    out["ex_ids"], out["ex_probs"] = res.doc_ids.astype(np.int64), res.probabilities
+    ex = np.full((len(queries), 10, 11), np.nan)
+    for qi, row in enumerate(res.explanations):
+        for ri, t in enumerate(row):
+            if t is not None:
+                ex[qi, ri] = [t.raw_score, t.tf, t.doc_len_ratio, t.likelihood, t.tf_prior, t.norm_prior, t.composite_prior,
+                              t.logit_likelihood, t.logit_prior, t.logit_base_rate, t.posterior]
+    out["ex_traces"] = ex
+    meta["explain"] = {"corpus_seed": 7, "queries": queries, "alpha": float(sc._transform.alpha),
+                       "beta": float(sc._transform.beta), "base_rate": float(sc._transform.base_rate)}
+    np.savez_compressed(os.path.join(HERE, "extras.npz"), **out)
+    with open(os.path.join(HERE, "extras.json"), "w") as f:
+        json.dump(meta, f)
+    print("extras.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if "--extras-only" in sys.argv:
+        extras()
+        sys.exit(0)
     probability_fusion()
     scorer_cases()
     config1()
     multifield_blockmax()
+    extras()
