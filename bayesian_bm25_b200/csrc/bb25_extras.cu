@@ -7,6 +7,7 @@
 //  * bb25_balanced_fusion: balanced_log_odds_fusion (fusion.py:283-343): both signals' logits min-max
 //    normalised over the candidate set, then weight * dense + (1 - weight) * sparse.
 #include "bb25_internal.cuh"
+#include "bb25_device.cuh"
 
 namespace bb25 {
 
@@ -43,15 +44,7 @@ __global__ void __launch_bounds__(256) match_counts_kernel(const int32_t *__rest
             const uint2 ent = tab_lookup(tab, tab.row[t], blk);
             const int len = (int)(ent.y & kBlkLenMask);
             if (len == 0) continue;
-            long long lo = indptr[t] + (long long)ent.x;
-            const long long end = lo + len;
-            long long hi = end;
-            while (lo < hi) {
-                const long long mid = (lo + hi) >> 1;
-                if ((uint32_t)indices[mid] < doc) lo = mid + 1;
-                else hi = mid;
-            }
-            if (lo < end && (uint32_t)indices[lo] == doc) c++;
+            if (slice_find(indices + indptr[t] + (long long)ent.x, len, doc, doc & ~(uint32_t)(kBlockDocs - 1)) >= 0) c++;
         }
     }
     out_tf[i] = c;

@@ -820,16 +820,10 @@ __device__ __forceinline__ void fused_select_one(const FusedSelectArgs &a, unsig
                         const uint2 ent = tab_lookup(ff.tab, trow[i], (int)(doc / (uint32_t)kBlockDocs));
                         const int len = (int)(ent.y & kBlkLenMask);
                         if (len) {
-                            long long lo = ip[i] + (long long)ent.x;
-                            const long long end = lo + len;
-                            long long hi = end;
-                            while (lo < hi) {
-                                const long long mid = (lo + hi) >> 1;
-                                if ((uint32_t)ff.indices[mid] < doc) lo = mid + 1;
-                                else hi = mid;
-                            }
-                            if (lo < end && (uint32_t)ff.indices[lo] == doc) {
-                                val = ff.data[lo];
+                            const long long s0 = ip[i] + (long long)ent.x;
+                            const int pos = slice_find(ff.indices + s0, len, doc, doc & ~(uint32_t)(kBlockDocs - 1));
+                            if (pos >= 0) {
+                                val = ff.data[s0 + pos];
                                 present = true;
                             }
                         }

@@ -400,15 +400,7 @@ __device__ inline int count_matched_terms(const SelectArgs &a, int q, uint32_t d
         const uint2 ent = tab_lookup(a.tab, a.tab.row[t], blk);
         const int len = (int)(ent.y & kBlkLenMask);
         if (len == 0) continue;
-        long long lo = a.indptr[t] + (long long)ent.x;
-        const long long end = lo + len;
-        long long hi = end;
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if ((uint32_t)a.indices[mid] < doc) lo = mid + 1;
-            else hi = mid;
-        }
-        if (lo < end && (uint32_t)a.indices[lo] == doc) c++;
+        if (slice_find(a.indices + a.indptr[t] + (long long)ent.x, len, doc, doc & ~(uint32_t)(kBlockDocs - 1)) >= 0) c++;
     }
     return c;
 }
@@ -434,15 +426,9 @@ __device__ inline float exact_score_warp(const SelectArgs &a, int q, uint32_t do
                 const uint2 ent = tab_lookup(a.tab, a.tab.row[t], blk);
                 const int len = (int)(ent.y & kBlkLenMask);
                 if (len) {
-                    long long lo = a.indptr[t] + (long long)ent.x;
-                    const long long end = lo + len;
-                    long long hi = end;
-                    while (lo < hi) {
-                        const long long mid = (lo + hi) >> 1;
-                        if ((uint32_t)a.indices[mid] < doc) lo = mid + 1;
-                        else hi = mid;
-                    }
-                    if (lo < end && (uint32_t)a.indices[lo] == doc) val = a.data[lo];
+                    const long long s0 = a.indptr[t] + (long long)ent.x;
+                    const int pos = slice_find(a.indices + s0, len, doc, doc & ~(uint32_t)(kBlockDocs - 1));
+                    if (pos >= 0) val = a.data[s0 + pos];
                 }
             }
         }
@@ -561,16 +547,10 @@ __device__ __forceinline__ void select_one(const SelectArgs &a, unsigned char *s
                             const uint2 ent = tab_lookup(a.tab, trow, (int)(id / (uint32_t)kBlockDocs));
                             const int len = (int)(ent.y & kBlkLenMask);
                             if (len) {
-                                long long lo = ip + (long long)ent.x;
-                                const long long end = lo + len;
-                                long long hi = end;
-                                while (lo < hi) {
-                                    const long long mid = (lo + hi) >> 1;
-                                    if ((uint32_t)a.indices[mid] < id) lo = mid + 1;
-                                    else hi = mid;
-                                }
-                                if (lo < end && (uint32_t)a.indices[lo] == id) {
-                                    val = a.data[lo];
+                                const long long s0 = ip + (long long)ent.x;
+                                const int pos = slice_find(a.indices + s0, len, id, id & ~(uint32_t)(kBlockDocs - 1));
+                                if (pos >= 0) {
+                                    val = a.data[s0 + pos];
                                     present = true;
                                 }
                             }
@@ -1479,6 +1459,8 @@ __global__ void __launch_bounds__(256) cand_kernel(const __grid_constant__ CandA
                     const uint2 ent = tab_lookup(a.tab, s_row[i], (int)(d >> 10));
                     const int len = (int)(ent.y & kBlkLenMask);
                     if (len) {
+                        // plain bisection: the threads of a warp search different terms' slices, and the uniform
+                        // trip count beats the data-dependent probing of slice_find here (measured)
                         long long lo = s_base[i] + (long long)ent.x;
                         const long long end = lo + len;
                         long long hi = end;

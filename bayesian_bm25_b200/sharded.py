@@ -307,8 +307,20 @@ class ShardedRetriever:
                 t.record_stream(main)
         return tuple(torch.cat([o[j] for o in outs], dim=0) for j in range(3))
 
-    def retrieve_ids(self, q_terms, q_off, k: int = 10, return_scores: bool = False):
-        """Host in / host out: every rank passes the same queries; every rank gets the merged result."""
+    def _to_host(self, outs, result: str):
+        """Merged device tensors -> page-locked host arrays on the ranks that want them."""
+        if result == "rank0" and self._sharded() and dist.get_rank(self.group) != 0:
+            torch.cuda.current_stream().synchronize()
+            return None
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+        for h, t in zip(host, outs):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return tuple(h.numpy() for h in host)
+
+    def retrieve_ids(self, q_terms, q_off, k: int = 10, return_scores: bool = False, result: str = "all"):
+        """Host in / host out: every rank passes the same queries.  result="all": every rank gets the merged
+        result; "rank0": only rank 0 copies it to the host (the others return None)."""
         q_terms = np.ascontiguousarray(q_terms, dtype=np.int32)
         q_off = np.ascontiguousarray(q_off, dtype=np.int64)
         dev = self.scorer._device
@@ -317,14 +329,44 @@ class ShardedRetriever:
         ho = torch.empty(q_off.size, dtype=torch.int64, pin_memory=True)
         ho.numpy()[:] = q_off
         ids, sc, pr = self.retrieve_ids_device(hp.to(dev, non_blocking=True), ho.to(dev, non_blocking=True), k, host_off=q_off)
-        outs = [ids, sc, pr] if return_scores else [ids, pr]
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
-        for h, t in zip(host, outs):
-            h.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return tuple(h.numpy() for h in host)
+        return self._to_host([ids, sc, pr] if return_scores else [ids, pr], result)
 
-    def retrieve(self, query_tokens: list[list[str]], k: int = 10):
-        """BayesianBM25Scorer.retrieve on the sharded index: (doc_ids [Q,k], probabilities [Q,k])."""
-        flat, off = self.scorer._term_ids_batch(query_tokens)
-        return self.retrieve_ids(flat, off, k)
+    def _term_ids_distributed(self, query_tokens):
+        """Token strings -> term ids with the work split over the ranks: rank r maps the queries
+        [r*Q/S, (r+1)*Q/S) through the vocabulary (Python dict lookups, ~2.5 us per query) and the ranks
+        all-gather the ids -- 1/S of the host-side mapping per rank.  Returns (flat ids on the device,
+        offsets on the host)."""
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        dev = self.scorer._device
+        nq = len(query_tokens)
+        qs = -(-nq // world)
+        lo, hi = min(nq, rank * qs), min(nq, (rank + 1) * qs)
+        flat, off = self.scorer._term_ids_batch(query_tokens[lo:hi])
+        lens = np.zeros(qs, dtype=np.int64)
+        lens[:hi - lo] = np.diff(off)
+        all_lens = torch.empty(world * qs, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_lens, torch.from_numpy(lens).to(dev), group=self.group)
+        all_lens_h = all_lens.cpu().numpy()
+        totals = all_lens_h.reshape(world, qs).sum(axis=1)
+        tmax = max(1, int(totals.max()))
+        mine = torch.zeros(tmax, dtype=torch.int32, device=dev)
+        if flat.size:
+            mine[:flat.size] = torch.from_numpy(flat).to(dev)
+        everyone = torch.empty(world * tmax, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        parts = [everyone[r * tmax:r * tmax + int(totals[r])] for r in range(world)]
+        d_flat = torch.cat(parts) if int(totals.sum()) else torch.zeros(1, dtype=torch.int32, device=dev)
+        off_h = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(all_lens_h[:nq], out=off_h[1:])
+        return d_flat, off_h
+
+    def retrieve(self, query_tokens: list[list[str]], k: int = 10, result: str = "all"):
+        """BayesianBM25Scorer.retrieve on the sharded index: (doc_ids [Q,k], probabilities [Q,k]) host arrays
+        (on rank 0 only with result="rank0").  Every rank passes the same token lists."""
+        if not self._sharded():
+            flat, off = self.scorer._term_ids_batch(query_tokens)
+            return self.retrieve_ids(flat, off, k)
+        d_flat, off_h = self._term_ids_distributed(query_tokens)
+        d_off = torch.from_numpy(off_h).to(self.scorer._device)
+        ids, _, pr = self.retrieve_ids_device(d_flat, d_off, k, host_off=off_h)
+        return self._to_host([ids, pr], result)

@@ -402,12 +402,13 @@ def main():
         in, host arrays out (token -> id mapping, H2D and D2H inside)."""
         if world == 1:
             return scorer.retrieve(query_tokens, args.k)
-        return retr.retrieve(query_tokens, args.k)  # every rank maps its own copy of the queries; results on rank 0
+        # the ranks split the token -> id mapping and all-gather the ids; the merged result goes to the caller on rank 0
+        return retr.retrieve(query_tokens, args.k, result="rank0")
 
     def e2e_ids_step():
         if world == 1:
             return scorer.retrieve_ids(q_terms, q_off, args.k)
-        return retr.retrieve_ids(q_terms, q_off, args.k)
+        return retr.retrieve_ids(q_terms, q_off, args.k, result="rank0")
 
     def timed_wall(fn):
         for _ in range(3):  # lets torch's pinned-host allocator settle on reusable blocks

@@ -157,8 +157,8 @@ def test_config1_vs_reference(golden_config1):
     assert probs.shape == (2, 3) and np.all(probs == 0.0)
     np.testing.assert_array_equal(ids, [[0, 1, 2], [0, 1, 2]])
     assert np.all(sc.get_probabilities(["xyznonexistent"]) == 0.0)
-    with pytest.raises(NotImplementedError):
-        sc.retrieve(queries[:1], k=3, explain=True)
+    res = sc.retrieve(queries[:1], k=3, explain=True)  # scorer.py:538-562; traces checked in test_gpu_extras.py
+    assert isinstance(res, pkg.RetrievalResult) and len(res.explanations) == 1 and len(res.explanations[0]) == 3
     n0 = sc.num_docs
     sc.add_documents([["term_1", "brandnewtoken"]], show_progress=False)
     assert sc.num_docs == n0 + 1

@@ -80,6 +80,17 @@ def _worker(rank, world, port, out_dir):
         ok = ok and np.array_equal(s_ids.numpy(), f_ids[:nq]) and np.array_equal(s_sc.numpy(), f_sc[:nq]) \
             and np.allclose(s_pr.numpy(), f_pr[:nq], rtol=0, atol=1e-15)
     ok = ok and retr.exchange_used.startswith("sliced: all_to_all_single")
+
+    # token -> id mapping split over the ranks and all-gathered (ShardedRetriever._term_ids_distributed)
+    from bayesian_bm25_b200.scorer import BayesianBM25Scorer
+    sc_ = BayesianBM25Scorer.__new__(BayesianBM25Scorer)
+    sc_._vocab = {f"t{i}": i for i in range(600)}
+    sc_._device = torch.device("cpu")
+    retr.scorer = sc_
+    toks = [[f"t{t}" for t in q_terms[q_off[i]:q_off[i + 1]]] + (["oov"] if i % 3 == 0 else []) for i in range(11)] + [[]]
+    d_flat, off_h = retr._term_ids_distributed(toks)
+    w_flat, w_off = sc_._term_ids_batch(toks)
+    ok = ok and np.array_equal(off_h, w_off) and np.array_equal(d_flat.numpy()[:w_flat.size], w_flat)
     with open(os.path.join(out_dir, f"rank{rank}.ok"), "w") as f:
         f.write("1" if ok else "0")
     dist.barrier()
