@@ -68,6 +68,8 @@ SIGNATURES = {
     "bb25_retrieve_one_dense": (_i32, [_vp, _PP, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bb25_retrieve_sync_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_index_set_threshold_exchange": (_i32, [_vp, _vp, _vp, _i32]),
+    "bb25_index_kth_values": (_i32, [_vp, _i32, C.POINTER(_vp), _vp]),
+    "bb25_index_set_kth_values": (_i32, [_vp, _i32, _vp, _vp]),
     "bb25_quantile_ranks": (None, [_i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "bb25_apply_quantiles": (_i32, [_i32, _vp, _i32, _i64, _i32, _vp, _vp]),
     "bb25_merge_topk_peers": (_i32, [_i32, _vp, _vp, _i32, _i64, _i64, _i32, _vp]),

@@ -167,6 +167,18 @@ __global__ void __launch_bounds__(256) build_dense_rows_kernel(const float *__re
     for (int64_t j = s + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < e; j += (int64_t)gridDim.x * blockDim.x)
         row[indices[j]] = data[j];
 }
+// fp16 upper-bound copy of the dense value rows; flag set when a value does not fit fp16
+__global__ void half_rows_kernel(const float *__restrict__ v, size_t n, __half *__restrict__ out, int *flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = v[i];
+    if (__float_as_uint(x) == 0x80000000u || x == 0.f) {
+        out[i] = __float2half_rn(0.f);
+        return;
+    }
+    if (x > 60000.f) atomicOr(flag, 1);
+    out[i] = __float2half_ru(x);
+}
 __global__ void fill_u32_kernel(unsigned int *p, size_t n, unsigned int v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -277,6 +289,19 @@ __global__ void __launch_bounds__(256) kth_value_kernel(const float *__restrict_
         if (threadIdx.x == 0) kth[t] = __uint_as_float(s_prefix);
         __syncthreads();
     }
+}
+
+// caller holds idx->mu
+int ensure_tile_table(bb25_index *idx, cudaStream_t st) {
+    if (idx->tile_off) return 0;
+    const size_t tt = (size_t)idx->n_vocab * (size_t)(idx->n_tiles + 1);
+    BB25_CUDA(cudaMalloc(&idx->tile_off, tt * sizeof(uint32_t)));
+    idx->device_bytes += tt * sizeof(uint32_t);
+    const int64_t blocks = (int64_t)((tt + 255) / 256);
+    build_tile_table_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx->indices, idx->indptr, idx->n_vocab, idx->n_tiles,
+                                                             idx->tile_docs, idx->tile_off);
+    BB25_LAUNCH_CHECK();
+    return 0;
 }
 
 int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out) {
@@ -401,19 +426,10 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
         return fail();
     }
 
+    // the per-(term, tile) offsets of the dense-output kernel are built on first use (ensure_tile_table):
+    // V x (N/8192 + 1) words -- 4 GB for a million-term vocabulary -- that batch retrieval never touches
     idx->tile_docs = pick_tile_docs();
     idx->n_tiles = (int)((n_docs + idx->tile_docs - 1) / idx->tile_docs);
-    size_t tt = (size_t)n_vocab * (size_t)(idx->n_tiles + 1);
-    TRY(cudaMalloc(&idx->tile_off, tt * sizeof(uint32_t)));
-    idx->device_bytes += tt * sizeof(uint32_t);
-    {
-        int64_t blocks = (int64_t)((tt + 255) / 256);
-        build_tile_table_kernel<<<(unsigned)blocks, 256>>>(idx->indices, idx->indptr, n_vocab, idx->n_tiles,
-                                                          idx->tile_docs, idx->tile_off);
-        count_launch();
-        TRY(cudaGetLastError());
-        TRY(cudaDeviceSynchronize());
-    }
     {
         idx->n_blocks = (int)((n_docs + kBlockDocs - 1) / kBlockDocs);
         // dense rows for every term while the table fits the budget; otherwise (or with
@@ -512,6 +528,26 @@ int bb25_index_create(int device, int64_t n_docs, int64_t n_vocab, int64_t nnz, 
             TRY(cudaGetLastError());
             TRY(cudaDeviceSynchronize());
             cudaFree(d_terms);
+            // fp16 upper-bound copy for the order-free pass (BB25_HALF_ROWS=0 at index creation: none)
+            const char *eh = getenv("BB25_HALF_ROWS");
+            if (!(eh && atoi(eh) == 0)) {
+                const size_t ne = (size_t)idx->n_dense * (size_t)idx->dense_stride;
+                int *hflag = nullptr;
+                TRY(cudaMalloc(&hflag, sizeof(int)));
+                TRY(cudaMemset(hflag, 0, sizeof(int)));
+                TRY(cudaMalloc(&idx->dense_h, ne * sizeof(__half)));
+                half_rows_kernel<<<(unsigned)((ne + 255) / 256), 256>>>(idx->dense_vals, ne, idx->dense_h, hflag);
+                count_launch();
+                int hf = 0;
+                TRY(cudaMemcpy(&hf, hflag, sizeof(int), cudaMemcpyDeviceToHost));
+                cudaFree(hflag);
+                if (hf) {  // values beyond the fp16 range: keep the fp32 rows only
+                    cudaFree(idx->dense_h);
+                    idx->dense_h = nullptr;
+                } else {
+                    idx->device_bytes += ne * sizeof(__half);
+                }
+            }
         }
     }
 #undef TRY
@@ -534,6 +570,7 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->tab_row);
     cudaFree(idx->dense_slot);
     cudaFree(idx->dense_vals);
+    cudaFree(idx->dense_h);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
     if (idx->ws) cudaFree(idx->ws);
     if (idx->hs_dev) cudaFree(idx->hs_dev);
@@ -544,6 +581,26 @@ void bb25_index_destroy(bb25_index *idx) {
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
     delete idx;
+}
+
+int bb25_index_kth_values(bb25_index *idx, int k, const float **out_dev, void *stream) {
+    if (!idx || !out_dev || k < 1) { set_error("bad arguments"); return 1; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("cannot select device"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    return get_kth_values(idx, k, (cudaStream_t)stream, out_dev);
+}
+
+int bb25_index_set_kth_values(bb25_index *idx, int k, const float *values_dev, void *stream) {
+    if (!idx || !values_dev || k < 1) { set_error("bad arguments"); return 1; }
+    DeviceGuard g(idx->device);
+    if (!g.ok) { set_error("cannot select device"); return 1; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    const float *cur = nullptr;
+    if (get_kth_values(idx, k, (cudaStream_t)stream, &cur)) return 1;
+    BB25_CUDA(cudaMemcpyAsync(const_cast<float *>(cur), values_dev, sizeof(float) * (size_t)idx->n_vocab, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+    return 0;
 }
 
 int bb25_index_info(const bb25_index *idx, int64_t *n_docs, int64_t *n_vocab, int64_t *nnz,

@@ -1,6 +1,7 @@
 // Internal declarations shared by the libbb25.so translation units.
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -244,6 +245,7 @@ struct bb25_index {
     // order-free traversal pass streams 128 bits per lane
     int32_t *dense_slot = nullptr;  // [n_vocab] slot or -1
     float *dense_vals = nullptr;    // [n_dense][dense_stride]
+    __half *dense_h = nullptr;      // the same rows as fp16 UPPER BOUNDS (rounded up, absent = 0): order-free pass only
     int n_dense = 0;
     int64_t dense_stride = 0;       // n_blocks * kBlockDocs
     std::map<int, float *> kth_cache;  // k -> fp32[n_vocab] k-th largest posting value per term
@@ -299,4 +301,5 @@ int prep_queries_launch(const bb25_index *idx, const int32_t *q_terms, const int
                         int64_t term_base, int64_t n_terms_total, int32_t *qt_ws, uint8_t *nocount, int64_t *qo_ws,
                         longlong2 *qt_info, int *err, cudaStream_t st);
 int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out);
+int ensure_tile_table(bb25_index *idx, cudaStream_t st);
 }  // namespace bb25

@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "bb25_internal.cuh"
 #include "bb25_device.cuh"
 
@@ -367,6 +369,9 @@ struct SelectArgs {
     // when at most sort_cap (<= kpad) valid keys are left, one bitonic sort replaces the 8-pass radix
     // select and the separate sort of the winners
     int sort_cap;
+    // pre-filter of the re-scoring: a new key below prefilter * (k-th largest key as it stands) cannot be among
+    // the best k; 1 - 3e-5 for fp32 order-free sums, 1 - 6e-4 when the sums come from fp16-bound rows
+    float prefilter;
     const float *data;
     const int32_t *indices;
     const int64_t *indptr;
@@ -499,7 +504,7 @@ __device__ __forceinline__ void select_one(const SelectArgs &a, unsigned char *s
         uint32_t cut_bits = 0u;
         if (n >= k && m <= 32) {
             const unsigned long long ta = block_kth_largest<NT>(keys, n, k, hist, st, tid, 3);  // top 24 bits: T rounded down
-            cut_bits = __float_as_uint(__fmul_rn(__uint_as_float(key_score_bits(ta)), 0.99997f));
+            cut_bits = __float_as_uint(__fmul_rn(__uint_as_float(key_score_bits(ta)), a.prefilter));
             __syncthreads();
         }
         uint16_t *list = reinterpret_cast<uint16_t *>(flag + kpad);
@@ -781,6 +786,7 @@ struct BlockArgs {
     int prune;  // 0 exhaustive, 1 block-max skip, 2 + skip of frequent-term-only documents by their bound
     const int32_t *dense_slot;
     const float *dense_vals;
+    const __half *dense_h;  // fp16 upper-bound copy of the dense rows (order-free pass only) or NULL
     int64_t dense_stride;
     unsigned long long *work_counter;
     unsigned long long *stats;  // [0] (block, query) units handed out, [1] units pruned by the block-max bound, [2] units under the level-2 restriction
@@ -911,10 +917,24 @@ __device__ __noinline__ void emit_quad_relaxed(float4 v, uint32_t first_id, uint
     }
 }
 
+// One quad (4 consecutive documents) of a D term's row.  HALF: the row of fp16 UPPER BOUNDS (values rounded
+// up at index creation, absent = 0) -- half the bytes and L1 wavefronts per quad; the sums formed from it are
+// upper bounds of the fp32 sums, which is all the order-free pass needs (every candidate it emits is
+// re-scored exactly).
+template <bool HALF>
+__device__ __forceinline__ float4 ld_row_quad(const unsigned char *row, int quad) {
+    if (!HALF) return ld_row_f4(reinterpret_cast<const float4 *>(row) + quad);
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(reinterpret_cast<const uint2 *>(row) + quad));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 struct PassArgs {
     float4 *acc4;          // the warp's accumulators, already offset by the lane
-    const float4 *row_a;   // first / second D term's value row at (block, lane)
-    const float4 *row_b;
+    const unsigned char *row_a;  // first / second D term's value row at (block, lane): fp32 or fp16-bound quads
+    const unsigned char *row_b;
     unsigned rest;         // third and later D terms (query positions)
     int dslot;             // lane i: dense slot of term i
     uint32_t thr_rel;      // relaxed threshold, >= 1
@@ -926,8 +946,9 @@ struct PassArgs {
 //   ND     D terms whose rows are added from registers (2 = two or more, the others via `rest`)
 //   HAS_S  the accumulators hold S-term sums: read them and leave zeros behind
 //   PRED   only quads with an S contribution are completed (D-only documents cannot qualify)
-template <int ND, bool HAS_S, bool PRED>
-__device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassArgs &pa, const float *dbase) {
+template <int ND, bool HAS_S, bool PRED, bool HALF>
+__device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassArgs &pa, const unsigned char *dbase) {
+    const size_t row_bytes = (size_t)a.dense_stride * (HALF ? 2 : 4);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll kPassUnroll
     for (int h = 0; h < kBlockDocs / (128 * kPassChunks); h++) {
@@ -942,12 +963,12 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
                 ra[j] = zero4;
                 rb[j] = zero4;
                 if (nz) {
-                    if (ND >= 1) ra[j] = ld_row_f4(pa.row_a + w);
-                    if (ND >= 2) rb[j] = ld_row_f4(pa.row_b + w);
+                    if (ND >= 1) ra[j] = ld_row_quad<HALF>(pa.row_a, w);
+                    if (ND >= 2) rb[j] = ld_row_quad<HALF>(pa.row_b, w);
                 }
             } else {
-                if (ND >= 1) ra[j] = ld_row_f4(pa.row_a + w);
-                if (ND >= 2) rb[j] = ld_row_f4(pa.row_b + w);
+                if (ND >= 1) ra[j] = ld_row_quad<HALF>(pa.row_a, w);
+                if (ND >= 2) rb[j] = ld_row_quad<HALF>(pa.row_b, w);
             }
             if (HAS_S) pa.acc4[w] = zero4;
         }
@@ -959,11 +980,11 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
         if (ND >= 2) {
             for (unsigned mm = pa.rest; mm; mm &= mm - 1) {  // third and later D terms
                 const int slot = __shfl_sync(0xFFFFFFFFu, pa.dslot, __ffs(mm) - 1);
-                const float4 *rp = reinterpret_cast<const float4 *>(dbase + (size_t)slot * (size_t)a.dense_stride);
+                const unsigned char *rp = dbase + (size_t)slot * row_bytes;
 #pragma unroll
                 for (int j = 0; j < kPassChunks; j++) {
                     if (!PRED || fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)) > 0.f)
-                        add_f4(v[j], ld_row_f4(rp + w0 + j * 32));
+                        add_f4(v[j], ld_row_quad<HALF>(rp, w0 + j * 32));
                 }
             }
         }
@@ -985,7 +1006,7 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
 #ifndef BB25_BLOCK_CTAS_PRUNED
 #define BB25_BLOCK_CTAS_PRUNED 4
 #endif
-template <int WARPS, bool EXACT, bool SPARSE_TAB, int CTAS>
+template <int WARPS, bool EXACT, bool SPARSE_TAB, int CTAS, bool HALF>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
@@ -1096,27 +1117,26 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
                     pa.q = q;
                     pa.rest = 0u;
                     pa.dslot = dslot;
-                    const float *dbase = a.dense_vals + doc_base + lane * 4;
-                    if (n_d >= 1)
-                        pa.row_a = reinterpret_cast<const float4 *>(
-                            dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(dmask) - 1) * (size_t)a.dense_stride);
+                    const size_t row_bytes = (size_t)a.dense_stride * (HALF ? 2 : 4);
+                    const unsigned char *dbase = HALF ? reinterpret_cast<const unsigned char *>(a.dense_h + doc_base + lane * 4)
+                                                      : reinterpret_cast<const unsigned char *>(a.dense_vals + doc_base + lane * 4);
+                    if (n_d >= 1) pa.row_a = dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(dmask) - 1) * row_bytes;
                     if (n_d >= 2) {
                         const unsigned d2 = dmask & (dmask - 1);
-                        pa.row_b = reinterpret_cast<const float4 *>(
-                            dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(d2) - 1) * (size_t)a.dense_stride);
+                        pa.row_b = dbase + (size_t)__shfl_sync(0xFFFFFFFFu, dslot, __ffs(d2) - 1) * row_bytes;
                         pa.rest = d2 & (d2 - 1);
                     }
                     if (!smask) {
-                        if (n_d == 1) order_free_pass<1, false, false>(a, pa, dbase);
-                        else order_free_pass<2, false, false>(a, pa, dbase);
+                        if (n_d == 1) order_free_pass<1, false, false, HALF>(a, pa, dbase);
+                        else order_free_pass<2, false, false, HALF>(a, pa, dbase);
                     } else if (n_d == 0) {
-                        order_free_pass<0, true, false>(a, pa, dbase);
+                        order_free_pass<0, true, false, HALF>(a, pa, dbase);
                     } else if (dense_all) {
-                        if (n_d == 1) order_free_pass<1, true, false>(a, pa, dbase);
-                        else order_free_pass<2, true, false>(a, pa, dbase);
+                        if (n_d == 1) order_free_pass<1, true, false, HALF>(a, pa, dbase);
+                        else order_free_pass<2, true, false, HALF>(a, pa, dbase);
                     } else {
-                        if (n_d == 1) order_free_pass<1, true, true>(a, pa, dbase);
-                        else order_free_pass<2, true, true>(a, pa, dbase);
+                        if (n_d == 1) order_free_pass<1, true, true, HALF>(a, pa, dbase);
+                        else order_free_pass<2, true, true, HALF>(a, pa, dbase);
                     }
                     __syncwarp();
                     continue;
@@ -1172,7 +1192,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
                     pa.q = q;
                     pa.rest = 0u;
                     pa.dslot = -1;
-                    order_free_pass<0, true, false>(a, pa, nullptr);
+                    order_free_pass<0, true, false, HALF>(a, pa, nullptr);
                     __syncwarp();
                     continue;
                 }
@@ -1228,21 +1248,22 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
     const bool sparse_tab = idx->tab_sparse_terms > 0;
-#define BB25_LAUNCH_BLOCK(EX, SP, CT)                                                                                 \
+#define BB25_LAUNCH_BLOCK(EX, SP, CT, HF)                                                                             \
     do {                                                                                                              \
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP, CT>,                                            \
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP, CT, HF>,                                        \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
-        block_kernel<BK_WARPS, EX, SP, CT><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                           \
+        block_kernel<BK_WARPS, EX, SP, CT, HF><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                       \
     } while (0)
+    const bool half_rows = !exact && a.dense_h != nullptr;
     if (exact) {
-        if (sparse_tab) BB25_LAUNCH_BLOCK(true, true, 6);
-        else BB25_LAUNCH_BLOCK(true, false, 6);
+        if (sparse_tab) BB25_LAUNCH_BLOCK(true, true, 6, false);
+        else BB25_LAUNCH_BLOCK(true, false, 6, false);
     } else if (pruned_cfg) {
-        if (sparse_tab) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS_PRUNED);
-        else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS_PRUNED);
+        if (sparse_tab) { if (half_rows) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS_PRUNED, true); else BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS_PRUNED, false); }
+        else { if (half_rows) BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS_PRUNED, true); else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS_PRUNED, false); }
     } else {
-        if (sparse_tab) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS);
-        else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS);
+        if (sparse_tab) { if (half_rows) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS, true); else BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS, false); }
+        else { if (half_rows) BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS, true); else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS, false); }
     }
 #undef BB25_LAUNCH_BLOCK
     BB25_LAUNCH_CHECK();
@@ -1603,6 +1624,7 @@ static int dense_workspace(bb25_index *idx, int n_terms, size_t extra, DenseWs &
 static int run_dense_staged(bb25_index *idx, int mode, const bb25_params *params, const DenseWs &w, int n_terms,
                             float *out_scores, double *out_probs, int64_t out_stride, cudaStream_t st,
                             const FuseSpec *fuse) {
+    if (ensure_tile_table(idx, st)) return 1;
     BB25_CUDA(cudaMemsetAsync(w.d_err, 0, sizeof(int), st));
     prep_queries_kernel<<<1, 32, 0, st>>>(w.d_src, w.d_qoff, 1, 0, n_terms, idx->n_vocab, nullptr, w.d_terms, w.d_nc, w.d_qo,
                                           nullptr, nullptr, nullptr, w.d_err);
@@ -1911,6 +1933,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         ng = 1;
     }
 
+    if (!use_block_kernel() && ensure_tile_table(idx, st)) return 1;
     TileArgs ta{};
     base_args(idx, ta);
     ta.q_terms = d_terms;
@@ -1945,6 +1968,10 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     if (const char *e = getenv("BB25_RELAXED")) relaxed = relaxed && atoi(e) != 0;
     ba.dense_slot = idx->dense_slot;
     ba.dense_vals = idx->dense_vals;
+    ba.dense_h = idx->dense_h;
+    if (const char *e = getenv("BB25_HALF_ROWS")) {
+        if (atoi(e) == 0) ba.dense_h = nullptr;
+    }
     ba.dense_stride = idx->dense_stride;
     ba.work_counter = d_work;
     ba.stats = d_stats;
@@ -1988,6 +2015,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     // at most kpad valid keys left (the usual case after the re-scoring pre-filter): one bitonic sort
     // replaces the 8-pass radix select plus the sort of the winners; more keys: radix select first
     sa.sort_cap = kpad;
+    // order-free sums formed from fp16-bound rows may exceed the exact score by up to 2^-11 relative per addend
+    sa.prefilter = ba.dense_h ? 0.9994f : 0.99997f;
     const size_t sel_smem = (size_t)cap * 10 + (size_t)kpad * 9 + 260 * 4;  // keys, top, hist+st, flag, rescore list
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     // grid of a select launch whose list length is only known on the device (repair rounds)

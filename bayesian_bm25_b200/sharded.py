@@ -128,6 +128,7 @@ class ShardedRetriever:
         self._quant_bufs: dict = {}
         self._symm: dict = {}    # (Qp, k) -> symmetric buffers and handles
         self._symm_failed = os.environ.get("BB25_SYMM", "1") == "0"
+        self._seeded: set = set()
         self.exchange_used = None
         self._install_threshold_exchange()
 
@@ -183,7 +184,43 @@ class ShardedRetriever:
             _lib.lib().bb25_index_set_threshold_exchange(self.scorer._handle, None, None, 0)
         self._cb = None
 
+    def _install_global_seeds(self, k: int) -> None:
+        """Once per k: every shard's per-term posting values at the ranks ceil(k/S), ceil(2k/S), ceil(4k/S), k
+        are all-gathered and combined into a lower bound of each term's k-th largest value over the WHOLE corpus
+        (bb25_apply_quantiles with terms in place of queries); the result replaces the shard's own threshold
+        seeds, so batches start with the seeds the unsharded index would use -- tighter thresholds in the first
+        block group and the same candidate-path routing decisions as a single GPU."""
+        if k in self._seeded or not (self._sharded() and self.threshold_exchange) or self.scorer._handle is None:
+            return
+        self._seeded.add(k)
+        lib = _lib.lib()
+        world = dist.get_world_size(self.group)
+        if world > 32:
+            return
+        dev = self.scorer._device
+        n_levels, ranks = C.c_int(), (C.c_int * 4)()
+        lib.bb25_quantile_ranks(k, world, C.byref(n_levels), ranks)
+        j = n_levels.value
+        v = self.scorer._n_vocab
+        cols = []
+        for r in list(ranks)[:j]:
+            ptr = C.c_void_p()
+            _lib.check(lib.bb25_index_kth_values(self.scorer._handle, int(r), C.byref(ptr), _lib.stream_ptr()))
+            t = torch.empty(v, dtype=torch.float32, device=dev)
+            _lib.check(lib.bb25_memcpy_device(dev.index, t.data_ptr(), ptr.value, v * 4, _lib.stream_ptr()))
+            cols.append(t)
+        mine = (torch.stack(cols, dim=1).contiguous().view(torch.int32).to(torch.int64) << 33)  # [V, J] score keys
+        everyone = torch.empty((world * v, j), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        bound = torch.zeros(v, dtype=torch.int64, device=dev)
+        _lib.check(lib.bb25_apply_quantiles(dev.index, everyone.data_ptr(), world, v, k, bound.data_ptr(), _lib.stream_ptr()))
+        seeds = (bound >> 33).to(torch.int32).view(torch.float32)
+        seeds = torch.maximum(seeds, cols[-1]).contiguous()  # never below the shard's own k-th value
+        _lib.check(lib.bb25_index_set_kth_values(self.scorer._handle, k, seeds.data_ptr(), _lib.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
     def _local(self, q_terms, q_off, k, host_off):
+        self._install_global_seeds(k)
         try:
             out = self.scorer.retrieve_ids_device(q_terms, q_off, k, host_off=host_off)
         except RuntimeError:

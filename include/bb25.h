@@ -176,6 +176,15 @@ void bb25_quantile_ranks(int k, int n_shards, int *n_levels, int *ranks4);
 int bb25_apply_quantiles(int device, const void *all_quantiles, int n_shards, int64_t n_queries, int k, void *d_thr,
                          void *stream);
 
+/* Threshold seeds.  bb25_index_kth_values: per term, the k-th largest posting value of THIS index (0 where the
+ * term has fewer than k postings) -- max over a query's terms bounds the query's k-th best score from below;
+ * the pointer (dev fp32 [n_vocab]) stays valid while the handle lives (a bounded cache keyed by k).
+ * bb25_index_set_kth_values replaces the cached values for k: a sharded deployment installs the bound that
+ * follows from ALL shards' values (k-th of the union >= any valid combination of per-shard ranks), so that a
+ * shard starts a batch with the global seed instead of its own, looser one.  Any lower bound is valid. */
+int bb25_index_kth_values(bb25_index *idx, int k, const float **out_dev, void *stream);
+int bb25_index_set_kth_values(bb25_index *idx, int k, const float *values_dev, void *stream);
+
 /* Exchange + merge in ONE kernel over peer memory (NVLink): this rank merges the queries
  * [q_begin, q_begin + n_queries).  src_tab_dev / dst_tab_dev: DEVICE arrays of n_shards pointers (symmetric
  * memory: entry s = rank s's buffer mapped into this process); every source buffer holds that shard's packed

@@ -536,25 +536,40 @@ def test_full_size_config2_properties():
     assert 3.9e8 < nnz < 4.3e8  # ~408 M postings
     sc = pkg.BayesianBM25Scorer(method="lucene", alpha=2.0, beta=0.2, base_rate=0.045)
     sc.index_from_csc(csc)
-    q_terms, q_off = synthetic.zipf_queries(256, vocab, seed=43)
-    ids, scores, probs = sc.retrieve_ids(q_terms, q_off, k, return_scores=True)
-    assert np.all(np.diff(scores.astype(np.float64), axis=1) <= 0)
-    ties = np.diff(scores.astype(np.float64), axis=1) == 0
-    assert np.all(np.diff(ids, axis=1)[ties] > 0)  # ties by ascending doc id
-    assert np.all((probs >= 0) & (probs <= 1))
-    # oracle on the first queries (CPU, seconds)
+    q_terms, q_off = synthetic.zipf_queries(253, vocab, seed=43)
+    # plus an all-head-term query, a duplicate-term query and a rare-term query
+    extra = [np.array([0, 1, 2, 3], np.int32), np.array([5, 5, 17, 5], np.int32), np.array([29999, 29998], np.int32)]
+    q_terms = np.concatenate([q_terms] + extra).astype(np.int32)
+    q_off = np.concatenate([q_off, q_off[-1] + np.cumsum([len(e) for e in extra])]).astype(np.int64)
+    # the oracle on 64 queries (the first 61 and the three special ones), CPU, seconds
     host = _host(csc)
     params = coracle.make_params(2.0, 0.2, 0.045)
-    nq = 24
-    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, q_terms[:q_off[nq]], q_off[:nq + 1], k)
-    np.testing.assert_array_equal(ids[:nq], o_ids)
-    np.testing.assert_array_equal(scores[:nq].view(np.uint32), o_sc.view(np.uint32))
-    np.testing.assert_allclose(probs[:nq], o_pr, rtol=0, atol=PROB_TOL)
+    sel = list(range(61)) + [253, 254, 255]
+    o_terms = np.concatenate([q_terms[q_off[i]:q_off[i + 1]] for i in sel]).astype(np.int32)
+    o_off = np.concatenate([[0], np.cumsum([q_off[i + 1] - q_off[i] for i in sel])]).astype(np.int64)
+    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, o_terms, o_off, k)
+    by_level = {}
+    for level in (0, 3):  # exhaustive (the headline mode) and the default pruning level
+        sc.set_pruning(level)
+        ids, scores, probs = sc.retrieve_ids(q_terms, q_off, k, return_scores=True)
+        by_level[level] = (ids, scores, probs)
+        assert np.all(np.diff(scores.astype(np.float64), axis=1) <= 0)
+        ties = np.diff(scores.astype(np.float64), axis=1) == 0
+        assert np.all(np.diff(ids, axis=1)[ties] > 0)  # ties by ascending doc id
+        assert np.all((probs >= 0) & (probs <= 1))
+        np.testing.assert_array_equal(ids[sel], o_ids)
+        np.testing.assert_array_equal(scores[sel].view(np.uint32), o_sc.view(np.uint32))
+        np.testing.assert_allclose(probs[sel], o_pr, rtol=0, atol=PROB_TOL)
+        assert sc.stats()["host_syncs"] <= 2
+    for a_, b_ in zip(by_level[0], by_level[3]):
+        np.testing.assert_array_equal(a_, b_)
+    ids, scores, probs = by_level[3]
     # dense scores agree with the retrieved ones
     q0 = q_terms[q_off[0]:q_off[1]]
     dense = sc.get_scores_ids(q0)
     np.testing.assert_array_equal(dense[ids[0]], scores[0])
     del host
+    nq = 0
     # shard union == unsharded (4 shards scored one after the other on this GPU, merged on device)
     parts = []
     dq, do = torch.from_numpy(q_terms).to(dev), torch.from_numpy(q_off).to(dev)
