@@ -106,6 +106,7 @@ SIGNATURES = {
     "bb25_attention_weights": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "bb25_attention_fuse": (_i32, [_i32, _vp, _i64, _i32, _vp, _i64, _dbl, _i32, _dbl, _i32, _vp, _vp]),
     "bb25_balanced_fusion": (_i32, [_i32, _vp, _vp, _i64, _dbl, _vp, _vp]),
+    "bb25_cosine_gemm": (_i32, [_i32, _vp, _i32, _vp, _i64, _i32, _vp, _i64, _vp]),
     "bb25_blockmax_dense": (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "bb25_blockmax_csc": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
 }

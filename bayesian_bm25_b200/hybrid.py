@@ -78,3 +78,26 @@ def hybrid_retrieve_batch_device(scorer, q_terms, q_off, cosine: torch.Tensor, k
 def hybrid_retrieve_batch(scorer, q_terms, q_off, cosine: torch.Tensor, k: int = 100, weights=(0.6, 0.4), alpha=None):
     ids, probs = hybrid_retrieve_batch_device(scorer, q_terms, q_off, cosine, k, weights, alpha)
     return ids.cpu().numpy(), probs.cpu().numpy()
+
+
+def hybrid_retrieve_batch_embeddings(scorer, q_terms, q_off, query_emb: torch.Tensor, corpus_emb: torch.Tensor,
+                                     k: int = 100, weights=(0.6, 0.4), alpha=None, sub_batch: int = 256):
+    """The whole hybrid step from embeddings: cosine GEMM on the tensor cores (dense.cosine_scores), then the
+    fused-rank batch retrieval, one sub-batch of queries at a time so that the transient [sub_batch, N] cosine
+    tile stays small.  Returns NumPy (ids int64 [Q,k], fused fp64 [Q,k])."""
+    import numpy as np
+
+    from . import dense
+    q_terms = np.ascontiguousarray(q_terms, dtype=np.int32)
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+    nq = q_off.size - 1
+    ids = np.empty((nq, k), dtype=np.int64)
+    probs = np.empty((nq, k), dtype=np.float64)
+    cos = None
+    for s in range(0, nq, sub_batch):
+        e = min(nq, s + sub_batch)
+        cos = dense.cosine_scores(query_emb[s:e], corpus_emb, out=cos[:e - s] if cos is not None else None)
+        i_, p_ = hybrid_retrieve_batch_device(scorer, q_terms[q_off[s]:q_off[e]], q_off[s:e + 1] - q_off[s], cos[:e - s],
+                                              k, weights, alpha)
+        ids[s:e], probs[s:e] = i_.cpu().numpy(), p_.cpu().numpy()
+    return ids, probs

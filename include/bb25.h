@@ -373,6 +373,14 @@ int bb25_attention_fuse(int device, const double *probs /*dev [m][n]*/, int64_t 
 int bb25_balanced_fusion(int device, const double *sparse_probs, const double *dense_similarities, int64_t n, double weight,
                          double *out, void *stream);
 
+/* Dense side of hybrid retrieval (benchmarks/hybrid_beir.py:1751-1753: query_emb @ corpus_emb.T): cosine
+ * similarities of up to 256 queries against every document, on the tensor cores (TMA + tcgen05.mma, fp32
+ * accumulation in tensor memory).  query_emb bf16 [n_queries][k], corpus_emb bf16 [n_docs][k] (dev, 16-byte
+ * aligned, rows L2-normalised by the caller, k a multiple of 64); out fp32 [n_queries][out_stride] (dev) --
+ * the cosine-row layout of bb25_retrieve_fused_batch. */
+int bb25_cosine_gemm(int device, const void *query_emb, int n_queries, const void *corpus_emb, int64_t n_docs, int k,
+                     float *out, int64_t out_stride, void *stream);
+
 /* ---- a12: BlockMaxIndex ---------------------------------------------------- */
 
 /* BlockMaxIndex.build (scorer.py:55-81) on a dense [n_terms][n_docs] fp64

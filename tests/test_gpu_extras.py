@@ -119,3 +119,46 @@ def test_retrieve_explain_vs_reference(gx):
     # explain=False keeps the tuple contract
     ids, probs = sc.retrieve(queries, k=10)
     np.testing.assert_array_equal(ids, res.doc_ids)
+
+
+def test_cosine_gemm_tcgen05_vs_torch_fp32():
+    """bb25_cosine_gemm (TMA + tcgen05.mma, fp32 accumulation in tensor memory) against a plain PyTorch fp32
+    matmul of the same bf16 inputs; tolerance: fp32 summation order over K terms."""
+    from bayesian_bm25_b200 import dense
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    for n, k, nq in ((5000, 128, 17), (128, 64, 1), (70001, 768, 256), (9000, 768, 300), (257, 192, 16)):
+        q = torch.nn.functional.normalize(torch.randn((nq, k), device="cuda", generator=g), dim=1).to(torch.bfloat16)
+        c = torch.nn.functional.normalize(torch.randn((n, k), device="cuda", generator=g), dim=1).to(torch.bfloat16)
+        got = dense.cosine_scores(q, c)
+        assert got.shape == (nq, (n + 3) // 4 * 4)
+        want = q.float() @ c.float().T
+        torch.testing.assert_close(got[:, :n], want, rtol=0, atol=2e-5)
+
+
+def test_hybrid_from_embeddings_vs_oracle():
+    """Embeddings -> tensor-core cosines -> fused-rank batch retrieval, against the oracle's conjunction of the
+    oracle's BM25 posterior and cosine_to_probability of the SAME cosines."""
+    import bayesian_bm25_b200 as pkg
+    from bayesian_bm25_b200 import dense, hybrid, synthetic
+    from oracle import coracle
+    n_docs, vocab, kdim = 30_000, 1500, 128
+    csc = synthetic.zipf_csc(n_docs, vocab, 40.0, seed=3, device=torch.device("cuda:0"))
+    host = {k_: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k_, v in csc.items()}
+    sc = pkg.BayesianBM25Scorer(alpha=1.8, beta=0.6, base_rate=0.02)
+    sc.index_from_csc(csc)
+    params = coracle.make_params(1.8, 0.6, 0.02)
+    terms, off = synthetic.zipf_queries(20, vocab, seed=8)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    qe = torch.nn.functional.normalize(torch.randn((20, kdim), device="cuda", generator=g), dim=1)
+    ce = torch.nn.functional.normalize(torch.randn((n_docs, kdim), device="cuda", generator=g), dim=1)
+    cos = dense.cosine_scores(qe, ce)[:, :n_docs].cpu().numpy()
+    ids, vals = hybrid.hybrid_retrieve_batch_embeddings(sc, terms, off, qe, ce, k=50, weights=(0.6, 0.4), alpha=0.5, sub_batch=8)
+    for q in range(20):
+        p_b = coracle.get_probabilities(host, params, terms[off[q]:off[q + 1]])
+        want = coracle.log_odds_conjunction(np.stack([p_b, coracle.cosine_to_probability(cos[q].astype(np.float64))], axis=-1),
+                                            alpha=0.5, weights=(0.6, 0.4))
+        w_ids, w_vals = coracle.topk_f64(want, 50)
+        np.testing.assert_allclose(vals[q], w_vals, rtol=0, atol=TOL)
+        assert np.array_equal(ids[q], w_ids) or np.max(np.abs(vals[q] - w_vals)) < 1e-12
