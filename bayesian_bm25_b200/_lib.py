@@ -101,6 +101,7 @@ SIGNATURES = {
     "bb25_retrieve_fused_batch": (_i32, [_i32, C.POINTER(FusedField), _vp, _i64, _dbl, _i32, _dbl, _i64, _i32, _vp, _vp, _vp]),
     "bb25_fused_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                                 C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_dbl)]),
+    "bb25_fused_prune_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_match_counts": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "bb25_trace_bm25": (_i32, [_i32, _PP, _vp, _vp, _vp, _i64, _vp, _vp]),
     "bb25_attention_weights": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -105,9 +105,11 @@ struct FusedBlockArgs {
     int blk_begin, blk_end;
     int prune;
     int pair_mode;  // two fields: both in one pass (A/B accumulators) instead of one fold pass per field
+    int sparse_mode;  // pair mode: essential-posting evaluation of units (pruning level >= 2)
     unsigned long long *work_counter;
     unsigned long long *stats;  // [0] units handed out, [1] skipped by the block bound, [2] abandoned between fields,
-                                // [3] evaluated under the frequent-term restriction
+                                // [3] evaluated under the frequent-term restriction, [4] skipped: no essential posting,
+                                // [5] evaluated through their essential postings, [6] documents evaluated that way
 };
 
 struct FTermEnt {
@@ -391,6 +393,113 @@ __device__ __forceinline__ void cos_only_pass(const FusedBlockArgs &a, int doc_b
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Essential-posting evaluation of a unit (two fields, no dense signal, pruning level >= 2): MaxScore
+// (the partition behind wand_upper_bound, probability.py:205-236) at the granularity of one 1024-document
+// block, on the fused key.
+//
+// The unit's (field, term) entries are split by the length of their slice in this block: NON-ESSENTIAL =
+// every entry with at least L postings here, for the smallest L of a fixed ladder whose entries' bound --
+// the unit bound of the block-max test restricted to that subset: per field ka * (sum of block maxima) + o,
+// capped -- stays below the threshold.  A document of the block that matches non-essential entries only
+// cannot qualify, so every qualifying document has a posting in one of the ESSENTIAL (short) slices: those
+// <= kSparseMax documents are evaluated one by one (S-term sums out of the accumulators, D-term values
+// gathered from the dense rows) instead of by a pass over all 1024 accumulators with the D rows streamed
+// in full; a unit without any essential posting is skipped outright.  Zipf queries carry a rare
+// term more often than not, and a rare term has a handful of postings per block: this is what prunes
+// where the block-max test alone cannot (nearly every block holds every frequent term near its maximum).
+// ---------------------------------------------------------------------------------
+constexpr int kSparseMax = 64;      // essential documents evaluated one by one; longer lists take the pass
+constexpr int kSparseCuts = 7;      // ladder L = 2, 3, 5, 9, 17, 33, 65
+
+// Returns the number of essential postings of the unit, or -1 when no subset of the ladder stays below the
+// threshold (the unit takes the pass).  `L_out` = the chosen split.
+__device__ __forceinline__ int essential_split(const FusedBlockArgs &a, const FTermEnt &e0, const FTermEnt &e1, int m0, int m1,
+                                               float o0, float o1, float thr, int lane, int &L_out) {
+    const int mycut = 1 + (1 << (lane & 7));  // lanes 0..6 own a ladder step each (lane 7 and up: duplicates)
+    float s0 = 0.f, s1 = 0.f;
+    bool any0 = false, any1 = false;
+    for (int t = 0; t < m0; t++) {
+        const int l = __shfl_sync(0xFFFFFFFFu, e0.len, t);
+        const float b = __shfl_sync(0xFFFFFFFFu, e0.bmax, t);
+        if (l >= mycut) {
+            s0 = __fadd_rn(s0, b);
+            any0 = true;
+        }
+    }
+    for (int t = 0; t < m1; t++) {
+        const int l = __shfl_sync(0xFFFFFFFFu, e1.len, t);
+        const float b = __shfl_sync(0xFFFFFFFFu, e1.bmax, t);
+        if (l >= mycut) {
+            s1 = __fadd_rn(s1, b);
+            any1 = true;
+        }
+    }
+    // same margins as the block-max test of the traversal
+    const float f0 = any0 ? fminf(__fmul_rn(__fmaf_rn(a.f[0].ka, __fmul_rn(s0, 1.000004f), o0), 1.000002f), a.f[0].ucap) : 0.f;
+    const float f1 = any1 ? fminf(__fmul_rn(__fmaf_rn(a.f[1].ka, __fmul_rn(s1, 1.000004f), o1), 1.000002f), a.f[1].ucap) : 0.f;
+    const bool pass = (lane & 7) < kSparseCuts && __fmul_rn(__fadd_rn(f0, f1), 1.000002f) < thr;
+    const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass) & 0x7Fu;
+    if (!pm) return -1;
+    const int L = 1 + (1 << (__ffs(pm) - 1));
+    L_out = L;
+    const int mine = ((e0.len > 0 && e0.len < L) ? e0.len : 0) + ((e1.len > 0 && e1.len < L) ? e1.len : 0);
+    return warp_sum(mine);
+}
+
+// Evaluate the documents of the essential slices of a unit whose S-term slices (essential or not) have
+// been scattered into the accumulators A (field 0) and B (field 1) and whose essential entries are all S
+// entries.  Lane = posting of one essential slice at a time (doc ids of a slice are distinct): the
+// document's S-term sums are read from the accumulators -- and zeroed, which marks it as done for the
+// other essential slices that hold it --, the D terms' values are gathered from their dense rows, the
+// bound is formed as in pair_pass.  The accumulators are cleared by the caller afterwards.
+__device__ __forceinline__ void sparse_walk(const FusedBlockArgs &a, const FTermEnt &e0, const FTermEnt &e1, int L,
+                                            float *A, float *B, unsigned dm0, unsigned dm1, float o0, float o1,
+                                            int doc_base, int lane, float thr, int q, const uint4 *sfd_q) {
+    const float *dv0 = a.f[0].dense_vals + doc_base;
+    const float *dv1 = a.f[1].dense_vals + doc_base;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const FTermEnt &e = i == 0 ? e0 : e1;
+        const int32_t *ind = a.f[i].indices;
+        for (unsigned mm = __ballot_sync(0xFFFFFFFFu, e.len > 0 && e.len < L); mm; mm &= mm - 1) {
+            const int t = __ffs(mm) - 1;
+            const int len = __shfl_sync(0xFFFFFFFFu, e.len, t);
+            const long long s = shfl_ll(e.start, t);
+            for (int j0 = 0; j0 < len; j0 += 32) {
+                bool act = false;
+                int o = 0;
+                float sa = 0.f, sb = 0.f;
+                if (j0 + lane < len) {
+                    o = ld_nc_s32(ind + s + j0 + lane) - doc_base;
+                    sa = A[o];
+                    sb = B[o];
+                    act = (sa != 0.f) || (sb != 0.f);  // both zero: evaluated already through another slice
+                    if (act) {
+                        A[o] = 0.f;
+                        B[o] = 0.f;
+                    }
+                }
+                for (unsigned m2 = dm0; m2; m2 &= m2 - 1) {
+                    const int slot = __shfl_sync(0xFFFFFFFFu, e0.dslot, __ffs(m2) - 1);
+                    if (act) sa = __fadd_rn(sa, dv0[(size_t)slot * (size_t)a.f[0].dense_stride + o]);  // absent: -0.0f
+                }
+                for (unsigned m2 = dm1; m2; m2 &= m2 - 1) {
+                    const int slot = __shfl_sync(0xFFFFFFFFu, e1.dslot, __ffs(m2) - 1);
+                    if (act) sb = __fadd_rn(sb, dv1[(size_t)slot * (size_t)a.f[1].dense_stride + o]);
+                }
+                if (act) {
+                    const float ua = sa > 0.f ? __fmaf_rn(a.f[0].ka, sa, o0) : 0.f;
+                    const float ub = sb > 0.f ? __fmaf_rn(a.f[1].ka, sb, o1) : 0.f;
+                    emit_one_fused(a, __fadd_rn(ua, ub), (sa > 0.f ? 1u : 0u) | (sb > 0.f ? 2u : 0u), (uint32_t)(doc_base + o), thr, q,
+                                   sfd_q);
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 // In FusedBlockArgs the fields are in TRAVERSAL order (cheapest index first): after each field but the last
 // the unit is abandoned when no document's running bound plus the remaining fields' block bounds can reach
 // the threshold -- the per-document version of the block-max test, far tighter because it uses the scores
@@ -418,7 +527,7 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
-    unsigned int skipped = 0u, abandoned = 0u, restricted = 0u;
+    unsigned int skipped = 0u, abandoned = 0u, restricted = 0u, ne_skipped = 0u, sparse_units = 0u, sparse_docs = 0u;
 
     for (;;) {
         long long item = 0;
@@ -495,6 +604,27 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
                 for (int i = 0; i < 2; i++) {
                     dm[i] = __ballot_sync(0xFFFFFFFFu, e[i].dslot >= 0);
                     sm[i] = pres[i] & ~dm[i];
+                }
+                // essential-posting evaluation (see essential_split): only when every essential entry is an S entry
+                bool sparse = false;
+                int L = 0;
+                if (!HAS_COS && a.prune >= 2 && a.sparse_mode && thr > 0.f) {
+                    const FTermEnt &e1 = e[F > 1 ? 1 : 0];
+                    const int n_e = essential_split(a, e[0], e1, (int)sfd_q[0].y, (int)sfd_q[F > 1 ? 1 : 0].y, ofs[0], ofs[F > 1 ? 1 : 0],
+                                                    thr, lane, L);
+                    if (n_e >= 0 && n_e <= kSparseMax &&
+                        !__ballot_sync(0xFFFFFFFFu, (e[0].dslot >= 0 && e[0].len < L) || (e1.dslot >= 0 && e1.len < L))) {
+                        if (n_e == 0) {
+                            ne_skipped++;
+                            continue;
+                        }
+                        sparse = true;
+                        sparse_units++;
+                        sparse_docs += (unsigned)n_e;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
                     float *acc = i == 0 ? reinterpret_cast<float *>(U4) : B;
                     bool fresh = true;
                     for (unsigned mm = sm[i]; mm; mm &= mm - 1) {
@@ -506,6 +636,20 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
                         fresh = false;
                         __syncwarp();
                     }
+                }
+                if (sparse) {
+                    sparse_walk(a, e[0], e[F > 1 ? 1 : 0], L, reinterpret_cast<float *>(U4), B, dm[0], dm[1], ofs[0], ofs[F > 1 ? 1 : 0],
+                                doc_base, lane, thr, q, sfd_q);
+                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 *A4z = reinterpret_cast<float4 *>(U4);
+                    if (sm[0])
+#pragma unroll
+                        for (int h = 0; h < kBlockDocs / 128; h++) A4z[h * 32 + lane] = zero4;
+                    if (sm[1])
+#pragma unroll
+                        for (int h = 0; h < kBlockDocs / 128; h++) B4[h * 32 + lane] = zero4;
+                    __syncwarp();
+                    continue;
                 }
                 // documents matching frequent (D) terms only: bounded by the D terms' block maxima in both fields
                 bool pred = false;
@@ -578,6 +722,9 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
         if (skipped) atomicAdd(&a.stats[1], (unsigned long long)skipped);
         if (abandoned) atomicAdd(&a.stats[2], (unsigned long long)abandoned);
         if (restricted) atomicAdd(&a.stats[3], (unsigned long long)restricted);
+        if (ne_skipped) atomicAdd(&a.stats[4], (unsigned long long)ne_skipped);
+        if (sparse_units) atomicAdd(&a.stats[5], (unsigned long long)sparse_units);
+        if (sparse_docs) atomicAdd(&a.stats[6], (unsigned long long)sparse_docs);
     }
 }
 
@@ -965,7 +1112,7 @@ __global__ void fused_mark_bad_kernel(const int32_t *__restrict__ list, const un
 }
 
 struct FusedReport {
-    unsigned long long n_cand, units, skipped, abandoned, restricted;
+    unsigned long long n_cand, units, skipped, abandoned, restricted, ne_skipped, sparse_units, sparse_docs;
     unsigned int n_fallback, reruns;
     int err;
     int pad;
@@ -987,6 +1134,9 @@ __global__ void fused_report_kernel(const uint8_t *__restrict__ flags, int64_t n
         r.skipped = stats[1];
         r.abandoned = stats[2];
         r.restricted = stats[3];
+        r.ne_skipped = stats[4];
+        r.sparse_units = stats[5];
+        r.sparse_docs = stats[6];
         r.n_fallback = s_n;
         unsigned int re = 0;
         for (int i = 0; i < n_round_cnt; i++) re += round_cnt[i];
@@ -1122,7 +1272,7 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         unsigned long long *d_work = (unsigned long long *)(ws + o_ctr);
         int *d_err = (int *)(ws + o_ctr + 16);
         unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
-        unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [4]
+        unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [8]
         unsigned int *d_round = (unsigned int *)(ws + o_ctr + 128);             // [stage][round]
         const int kRoundStride = 8;
         FusedReport *d_report = (FusedReport *)(ws + o_ctr + 512);
@@ -1257,6 +1407,8 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         ba.prune = idx0->prune;
         ba.pair_mode = n_fields == 2 ? 1 : 0;
         if (const char *e = getenv("BB25_FUSED_PAIR")) ba.pair_mode = (n_fields == 2 && atoi(e) != 0) ? 1 : 0;
+        ba.sparse_mode = 1;
+        if (const char *e = getenv("BB25_FUSED_SPARSE")) ba.sparse_mode = atoi(e) != 0 ? 1 : 0;
         ba.work_counter = d_work;
         ba.stats = d_stats;
         float trav_ms = 0.f;
@@ -1310,6 +1462,9 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         idx0->fz_units = (int64_t)h_rep->units;
         idx0->fz_skipped = (int64_t)h_rep->skipped;
         idx0->fz_abandoned = (int64_t)h_rep->abandoned + (int64_t)h_rep->restricted;
+        idx0->fz_ne_skipped = (int64_t)h_rep->ne_skipped;
+        idx0->fz_sparse_units = (int64_t)h_rep->sparse_units;
+        idx0->fz_sparse_docs = (int64_t)h_rep->sparse_docs;
         idx0->fz_candidates = (int64_t)h_rep->n_cand;
         idx0->fz_fallback = (int64_t)h_rep->n_fallback;
         idx0->fz_reruns = (int64_t)h_rep->reruns;
@@ -1377,6 +1532,14 @@ int bb25_fused_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipp
     if (rerun_queries) *rerun_queries = idx->fz_reruns;
     if (host_syncs) *host_syncs = idx->fz_syncs;
     if (traverse_ms) *traverse_ms = idx->fz_traverse_ms;
+    return 0;
+}
+
+int bb25_fused_prune_stats(const bb25_index *idx, int64_t *units_no_essential, int64_t *units_sparse, int64_t *sparse_documents) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (units_no_essential) *units_no_essential = idx->fz_ne_skipped;
+    if (units_sparse) *units_sparse = idx->fz_sparse_units;
+    if (sparse_documents) *sparse_documents = idx->fz_sparse_docs;
     return 0;
 }
 

@@ -271,6 +271,7 @@ struct bb25_index {
     int64_t st_dense_fallback = 0;  // ... the dense guaranteed path
     // stats of the last bb25_retrieve_fused_batch whose first field is this index
     int64_t fz_units = 0, fz_skipped = 0, fz_abandoned = 0, fz_candidates = 0, fz_fallback = 0, fz_reruns = 0, fz_syncs = 0;
+    int64_t fz_ne_skipped = 0, fz_sparse_units = 0, fz_sparse_docs = 0;
     double fz_traverse_ms = 0.0;
     // device + stream of the host-buffer entry points (grow-only, reused across calls)
     void *hs_dev = nullptr;

@@ -105,4 +105,7 @@ def fused_stats(scorer) -> dict:
     names = ("units", "units_skipped", "units_abandoned", "candidates", "fallback_queries", "rerun_queries", "host_syncs")
     out = dict(zip(names, (x.value for x in v)))
     out["traverse_ms"] = ms.value
+    w = [C.c_int64() for _ in range(3)]
+    _lib.check(_lib.lib().bb25_fused_prune_stats(scorer._handle, *[C.byref(x) for x in w]))
+    out.update(zip(("units_no_essential", "units_sparse", "sparse_documents"), (x.value for x in w)))
     return out

@@ -200,6 +200,14 @@ def run(args, cpu_only: bool = False):
     pruned = measure(3)
     clocks = sampler.stop()
     exhaustive = measure(0)
+    no_sparse = None
+    if args.config == 5 and os.environ.get("BB25_BENCH_AB_SPARSE", "1") != "0":
+        # A/B inside the same process: level 3 without the essential-posting evaluation of units
+        os.environ["BB25_FUSED_SPARSE"] = "0"
+        try:
+            no_sparse = measure(3)
+        finally:
+            del os.environ["BB25_FUSED_SPARSE"]
     same = all(bool(torch.equal(x, y)) for x, y in zip(pruned["out"], exhaustive["out"]))
     head = pruned if args.config == 5 else exhaustive  # config 5 is the pruned configuration; config 4 is exhaustive
     qps = n_q * args.steps / (head["ms"] / 1000.0)
@@ -230,6 +238,9 @@ def run(args, cpu_only: bool = False):
         "pruned": {"value": n_q * args.steps / (pruned["ms"] / 1000.0), "ms_per_step": pruned["ms"] / args.steps,
                    "kernel_ms_per_step": pruned["traverse_ms"], "units_per_step": pruned["units"],
                    "units_skipped_per_step": pruned["units_skipped"], "units_abandoned_per_step": pruned["units_abandoned"],
+                   "units_no_essential_posting_per_step": pruned["units_no_essential"],
+                   "units_by_essential_postings_per_step": pruned["units_sparse"],
+                   "documents_evaluated_by_essential_postings_per_step": pruned["sparse_documents"],
                    "results_identical_to_exhaustive": same},
         "exhaustive": {"value": n_q * args.steps / (exhaustive["ms"] / 1000.0), "ms_per_step": exhaustive["ms"] / args.steps,
                        "kernel_ms_per_step": exhaustive["traverse_ms"], "units_per_step": exhaustive["units"]},
@@ -246,6 +257,71 @@ def run(args, cpu_only: bool = False):
                     "effective figure, not a DRAM fraction); the ncu counters of this kernel are under profiles/r02",
         },
     })
+    if no_sparse is not None:
+        line["pruned_without_essential_evaluation"] = {
+            "value": n_q * args.steps / (no_sparse["ms"] / 1000.0), "ms_per_step": no_sparse["ms"] / args.steps,
+            "kernel_ms_per_step": no_sparse["traverse_ms"],
+            "results_identical": all(bool(torch.equal(x, y)) for x, y in zip(no_sparse["out"], exhaustive["out"]))}
+    if args.config == 4:
+        # the dense side from embeddings: tcgen05 cosine GEMM (bb25_cosine_gemm) + the same fused retrieval
+        try:
+            from bayesian_bm25_b200 import dense
+            kdim = 768
+            del d_cos
+            torch.cuda.empty_cache()
+            gq = torch.Generator(device=dev)
+            gq.manual_seed(45)
+            ce = torch.empty((n_docs, kdim), dtype=torch.bfloat16, device=dev)
+            for s_ in range(0, n_docs, 1 << 20):
+                e_ = min(n_docs, s_ + (1 << 20))
+                ce[s_:e_] = torch.nn.functional.normalize(torch.randn((e_ - s_, kdim), device=dev, generator=gq), dim=1).to(torch.bfloat16)
+            qe_host = torch.nn.functional.normalize(torch.randn((n_q, kdim), generator=torch.Generator().manual_seed(46)), dim=1).to(torch.bfloat16).pin_memory()
+            qe = qe_host.to(dev)
+            cos_buf = dense.cosine_scores(qe[:256], ce)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            ev0.record()
+            for _ in range(reps):
+                for s_ in range(0, n_q, 256):
+                    dense.cosine_scores(qe[s_:s_ + 256], ce, out=cos_buf[:min(256, n_q - s_)])
+            ev1.record()
+            torch.cuda.synchronize()
+            gemm_ms = ev0.elapsed_time(ev1) / reps
+            flops = 2.0 * n_q * n_docs * kdim
+            peaks_json = {}
+            pth = os.path.join(B.ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(pth):
+                peaks_json = json.load(open(pth))
+            tf_peak = float(peaks_json.get("bf16_tflops_sustained", 1400.0))
+            want = (qe[:8].float() @ ce[:4096].float().T)
+            got = dense.cosine_scores(qe[:8], ce[:4096])[:, :4096]
+            gerr = float((got - want).abs().max())
+
+            def hyb_step():
+                return hybrid.hybrid_retrieve_batch_embeddings(scorers[0], flat, qoff, qe_host.to(dev, non_blocking=True), ce, k,
+                                                               weights=(weights[0], cos_w), alpha=alpha, sub_batch=256)
+            hyb_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                hyb_step()
+            torch.cuda.synchronize()
+            hyb_s = (time.perf_counter() - t0) / args.steps
+            line["dense_side"] = {
+                "what": "bb25_cosine_gemm: bf16 query_emb[%d,%d] @ corpus_emb[%d,%d]^T on tcgen05 / TMEM / TMA, fp32 cosine rows out; "
+                        "random unit embeddings" % (n_q, kdim, n_docs, kdim),
+                "gemm_ms_per_batch": gemm_ms, "tflops": flops / (gemm_ms * 1e-3) / 1e12, "peak_tflops": tf_peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks_json else "fallback",
+                "frac_of_bf16_peak": flops / (gemm_ms * 1e-3) / 1e12 / tf_peak,
+                "hbm_bytes_per_batch": int(-(-n_q // 256) * n_docs * kdim * 2 + n_q * n_docs * 4),
+                "hbm_gbs": (-(-n_q // 256) * n_docs * kdim * 2 + n_q * n_docs * 4) / (gemm_ms * 1e-3) / 1e9,
+                "max_abs_err_vs_torch_fp32": gerr,
+                "hybrid_from_embeddings_qps_e2e": n_q / hyb_s,
+                "hybrid_call": "hybrid_retrieve_batch_embeddings: query embeddings + term ids up from the host, GEMM, fused-rank batch retrieval, (ids, fused) back",
+            }
+        except Exception as e:  # the dense leg is an extra; never lose the bench line to it
+            line["dense_side"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
         ids = head["out"][0][:len(oracle_rows)].cpu().numpy()

@@ -346,6 +346,12 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
 int bb25_fused_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped, int64_t *units_abandoned,
                      int64_t *candidates, int64_t *fallback_queries, int64_t *rerun_queries, int64_t *host_syncs,
                      double *traverse_ms);
+/* essential-posting evaluation (two fields, no dense signal, pruning level >= 2: MaxScore's split --
+ * the partition behind wand_upper_bound, probability.py:205-236 -- per 1024-document block): units
+ * skipped because no essential slice has a posting in the block, units evaluated through their essential
+ * postings instead of a pass over the block, documents evaluated that way */
+int bb25_fused_prune_stats(const bb25_index *idx, int64_t *units_no_essential, int64_t *units_sparse,
+                           int64_t *sparse_documents);
 
 /* ---- query-time consumers of the probabilities ------------------- */
 
