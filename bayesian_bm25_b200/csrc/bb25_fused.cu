@@ -60,6 +60,8 @@ struct FField {
     const int64_t *indptr;
     BlockTable tab;
     const float *dense_vals;
+    const float *lookup_vals;  // value rows of the mid-frequency terms (bb25_index::lookup_vals) or NULL
+    int n_hot;                 // row slots below this are rows of dense_vals, the others rows of lookup_vals
     int64_t dense_stride;
     const int32_t *doc_len;
     double avgdl;
@@ -116,7 +118,9 @@ struct FTermEnt {
     long long start;
     int len;
     float bmax;
-    int dslot;
+    int dslot;    // hot (dense) row: the passes add it in registers
+    int rslot;    // any value row (hot or lookup): document-at-a-time evaluation reads it
+    uint32_t pk;  // the table entry's packed (block maximum | length) word
 };
 
 __device__ __forceinline__ FTermEnt fused_load_entry(const FField &ff, int blk, long long pos, bool active) {
@@ -125,14 +129,18 @@ __device__ __forceinline__ FTermEnt fused_load_entry(const FField &ff, int blk, 
     e.len = 0;
     e.bmax = 0.f;
     e.dslot = -1;
+    e.rslot = -1;
+    e.pk = 0u;
     if (active) {
-        const longlong2 info = ff.qt_info[2 * pos];      // (indptr[t], dense slot)
+        const longlong2 info = ff.qt_info[2 * pos];      // (indptr[t], hot slot | any-row slot << 32)
         const longlong2 trow = ff.qt_info[2 * pos + 1];  // the term's block-table row
         const uint2 ent = tab_lookup(ff.tab, trow, blk);
+        e.pk = ent.y;
         e.len = (int)(ent.y & kBlkLenMask);
         e.bmax = __uint_as_float(ent.y & ~kBlkLenMask);
         e.start = info.x + (long long)ent.x;
         e.dslot = e.len > 0 ? (int)info.y : -1;
+        e.rslot = e.len > 0 ? (int)(info.y >> 32) : -1;
     }
     return e;
 }
@@ -398,106 +406,180 @@ __device__ __forceinline__ void cos_only_pass(const FusedBlockArgs &a, int doc_b
 // (the partition behind wand_upper_bound, probability.py:205-236) at the granularity of one 1024-document
 // block, on the fused key.
 //
-// The unit's (field, term) entries are split by the length of their slice in this block: NON-ESSENTIAL =
-// every entry with at least L postings here, for the smallest L of a fixed ladder whose entries' bound --
-// the unit bound of the block-max test restricted to that subset: per field ka * (sum of block maxima) + o,
+// The unit's (field, term) entries are split: NON-ESSENTIAL = the entries that have a value row (hot or
+// lookup) and at least L postings in this block, for the smallest L of a fixed ladder whose bound -- the
+// unit bound of the block-max test restricted to that subset: per field ka * (sum of block maxima) + o,
 // capped -- stays below the threshold.  A document of the block that matches non-essential entries only
-// cannot qualify, so every qualifying document has a posting in one of the ESSENTIAL (short) slices: those
-// <= kSparseMax documents are evaluated one by one (S-term sums out of the accumulators, D-term values
-// gathered from the dense rows) instead of by a pass over all 1024 accumulators with the D rows streamed
-// in full; a unit without any essential posting is skipped outright.  Zipf queries carry a rare
-// term more often than not, and a rare term has a handful of postings per block: this is what prunes
-// where the block-max test alone cannot (nearly every block holds every frequent term near its maximum).
+// cannot qualify, so every qualifying document has a posting in one of the ESSENTIAL slices (row-less
+// terms, and row terms with fewer than L postings here).  When those slices hold at most 32 postings the
+// unit is evaluated document-at-a-time in ONE round: lane = essential posting (doc id and value straight
+// from the slice), postings of the same document are combined with a warp match, each non-essential
+// term's value is one 4-byte load from its row -- no accumulators, no scatter, no pass over 1024
+// documents.  Zipf queries carry a rare term more often than not, and a rare term has a handful of
+// postings per block: this prunes where the block-max test alone cannot (nearly every block holds every
+// frequent term near its maximum).  The ladder's last step is the full entry set: the block-max skip test
+// of the traversal, folded in.
 // ---------------------------------------------------------------------------------
-constexpr int kSparseMax = 64;      // essential documents evaluated one by one; longer lists take the pass
-constexpr int kSparseCuts = 7;      // ladder L = 2, 3, 5, 9, 17, 33, 65
+constexpr int kSparseMax = 32;  // essential postings evaluated in one round; longer lists take the pass
 
-// Returns the number of essential postings of the unit, or -1 when no subset of the ladder stays below the
-// threshold (the unit takes the pass).  `L_out` = the chosen split.
-__device__ __forceinline__ int essential_split(const FusedBlockArgs &a, const FTermEnt &e0, const FTermEnt &e1, int m0, int m1,
-                                               float o0, float o1, float thr, int lane, int &L_out) {
-    const int mycut = 1 + (1 << (lane & 7));  // lanes 0..6 own a ladder step each (lane 7 and up: duplicates)
-    float s0 = 0.f, s1 = 0.f;
-    bool any0 = false, any1 = false;
-    for (int t = 0; t < m0; t++) {
-        const int l = __shfl_sync(0xFFFFFFFFu, e0.len, t);
-        const float b = __shfl_sync(0xFFFFFFFFu, e0.bmax, t);
-        if (l >= mycut) {
-            s0 = __fadd_rn(s0, b);
-            any0 = true;
-        }
-    }
-    for (int t = 0; t < m1; t++) {
-        const int l = __shfl_sync(0xFFFFFFFFu, e1.len, t);
-        const float b = __shfl_sync(0xFFFFFFFFu, e1.bmax, t);
-        if (l >= mycut) {
-            s1 = __fadd_rn(s1, b);
-            any1 = true;
-        }
-    }
-    // same margins as the block-max test of the traversal
-    const float f0 = any0 ? fminf(__fmul_rn(__fmaf_rn(a.f[0].ka, __fmul_rn(s0, 1.000004f), o0), 1.000002f), a.f[0].ucap) : 0.f;
-    const float f1 = any1 ? fminf(__fmul_rn(__fmaf_rn(a.f[1].ka, __fmul_rn(s1, 1.000004f), o1), 1.000002f), a.f[1].ucap) : 0.f;
-    const bool pass = (lane & 7) < kSparseCuts && __fmul_rn(__fadd_rn(f0, f1), 1.000002f) < thr;
-    const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass) & 0x7Fu;
-    if (!pm) return -1;
-    const int L = 1 + (1 << (__ffs(pm) - 1));
-    L_out = L;
-    const int mine = ((e0.len > 0 && e0.len < L) ? e0.len : 0) + ((e1.len > 0 && e1.len < L) ? e1.len : 0);
-    return warp_sum(mine);
+__device__ __forceinline__ float row_value(const FField &ff, int rslot, uint32_t doc) {
+    return rslot < ff.n_hot ? ff.dense_vals[(size_t)rslot * (size_t)ff.dense_stride + doc]
+                            : ff.lookup_vals[(size_t)(rslot - ff.n_hot) * (size_t)ff.dense_stride + doc];  // absent: -0.0f
 }
 
-// Evaluate the documents of the essential slices of a unit whose S-term slices (essential or not) have
-// been scattered into the accumulators A (field 0) and B (field 1) and whose essential entries are all S
-// entries.  Lane = posting of one essential slice at a time (doc ids of a slice are distinct): the
-// document's S-term sums are read from the accumulators -- and zeroed, which marks it as done for the
-// other essential slices that hold it --, the D terms' values are gathered from their dense rows, the
-// bound is formed as in pair_pass.  The accumulators are cleared by the caller afterwards.
-__device__ __forceinline__ void sparse_walk(const FusedBlockArgs &a, const FTermEnt &e0, const FTermEnt &e1, int L,
-                                            float *A, float *B, unsigned dm0, unsigned dm1, float o0, float o1,
-                                            int doc_base, int lane, float thr, int q, const uint4 *sfd_q) {
-    const float *dv0 = a.f[0].dense_vals + doc_base;
-    const float *dv1 = a.f[1].dense_vals + doc_base;
+// One round of document-at-a-time evaluation for the queries of `batch` (a mask of 8-lane groups whose
+// essential postings add up to at most 32): lane = essential posting.
+__device__ __forceinline__ void sparse_round(const FusedBlockArgs &a, const FTermEnt &e0, const FTermEnt &e1, bool sparse_q, int L,
+                                             float thr_l, float o0, float o1, unsigned batch, int mmax, int s0, const uint4 *sfd,
+                                             const uint2 *sq, int doc_base, int lane) {
+    int o = -1, fld = 0, qid = 0, fill = 0;
+    float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const FTermEnt &e = i == 0 ? e0 : e1;
-        const int32_t *ind = a.f[i].indices;
-        for (unsigned mm = __ballot_sync(0xFFFFFFFFu, e.len > 0 && e.len < L); mm; mm &= mm - 1) {
-            const int t = __ffs(mm) - 1;
-            const int len = __shfl_sync(0xFFFFFFFFu, e.len, t);
-            const long long s = shfl_ll(e.start, t);
-            for (int j0 = 0; j0 < len; j0 += 32) {
-                bool act = false;
-                int o = 0;
-                float sa = 0.f, sb = 0.f;
-                if (j0 + lane < len) {
-                    o = ld_nc_s32(ind + s + j0 + lane) - doc_base;
-                    sa = A[o];
-                    sb = B[o];
-                    act = (sa != 0.f) || (sb != 0.f);  // both zero: evaluated already through another slice
-                    if (act) {
-                        A[o] = 0.f;
-                        B[o] = 0.f;
-                    }
-                }
-                for (unsigned m2 = dm0; m2; m2 &= m2 - 1) {
-                    const int slot = __shfl_sync(0xFFFFFFFFu, e0.dslot, __ffs(m2) - 1);
-                    if (act) sa = __fadd_rn(sa, dv0[(size_t)slot * (size_t)a.f[0].dense_stride + o]);  // absent: -0.0f
-                }
-                for (unsigned m2 = dm1; m2; m2 &= m2 - 1) {
-                    const int slot = __shfl_sync(0xFFFFFFFFu, e1.dslot, __ffs(m2) - 1);
-                    if (act) sb = __fadd_rn(sb, dv1[(size_t)slot * (size_t)a.f[1].dense_stride + o]);
-                }
-                if (act) {
-                    const float ua = sa > 0.f ? __fmaf_rn(a.f[0].ka, sa, o0) : 0.f;
-                    const float ub = sb > 0.f ? __fmaf_rn(a.f[1].ka, sb, o1) : 0.f;
-                    emit_one_fused(a, __fadd_rn(ua, ub), (sa > 0.f ? 1u : 0u) | (sb > 0.f ? 2u : 0u), (uint32_t)(doc_base + o), thr, q,
-                                   sfd_q);
-                }
-                __syncwarp();
+        const bool ess = sparse_q && e.len > 0 && (e.rslot < 0 || e.len < L);
+        for (unsigned mm = __ballot_sync(0xFFFFFFFFu, ess) & batch; mm; mm &= mm - 1) {
+            const int src = __ffs(mm) - 1;
+            const int len = __shfl_sync(0xFFFFFFFFu, e.len, src);
+            const long long s = shfl_ll(e.start, src);
+            const int r = lane - fill;
+            if (r >= 0 && r < len) {
+                o = ld_nc_s32(a.f[i].indices + s + r) - doc_base;
+                v = ld_nc_f32(a.f[i].data + s + r);
+                fld = i;
+                qid = src >> 3;
             }
+            fill += len;
         }
     }
+    const bool valid = o >= 0;
+    // postings of one (query, document) -- several essential slices may hold it -- are summed per field by the first lane
+    const unsigned g = __match_any_sync(0xFFFFFFFFu, valid ? ((qid << 10) | o) : (0x10000 | lane));
+    const int rounds = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)__popc(g));
+    float sa = 0.f, sb = 0.f;
+    unsigned rem = g;
+    for (int r = 0; r < rounds; r++) {
+        const int src = rem ? __ffs(rem) - 1 : lane;
+        const float vv = __shfl_sync(0xFFFFFFFFu, v, src);
+        const int ff = __shfl_sync(0xFFFFFFFFu, fld, src);
+        if (rem) {
+            if (ff) sb = __fadd_rn(sb, vv);
+            else sa = __fadd_rn(sa, vv);
+            rem &= rem - 1;
+        }
+    }
+    const bool leader = valid && (__ffs(g) - 1 == lane);
+    const uint32_t doc = (uint32_t)(doc_base + (valid ? o : 0));
+    const int ql = qid << 3;  // first lane of the posting's query
+    const int Lq = __shfl_sync(0xFFFFFFFFu, L, ql);
+    const float thrq = __shfl_sync(0xFFFFFFFFu, thr_l, ql);
+    const float o0q = __shfl_sync(0xFFFFFFFFu, o0, ql), o1q = __shfl_sync(0xFFFFFFFFu, o1, ql);
+    // the non-essential terms of the posting's query: one load from the term's value row each
+    for (int t = 0; t < mmax; t++) {
+        const int src = ql | t;
+        const int rs0 = __shfl_sync(0xFFFFFFFFu, e0.rslot, src), l0 = __shfl_sync(0xFFFFFFFFu, e0.len, src);
+        const int rs1 = __shfl_sync(0xFFFFFFFFu, e1.rslot, src), l1 = __shfl_sync(0xFFFFFFFFu, e1.len, src);
+        if (leader && rs0 >= 0 && l0 >= Lq) sa = __fadd_rn(sa, row_value(a.f[0], rs0, doc));
+        if (leader && rs1 >= 0 && l1 >= Lq) sb = __fadd_rn(sb, row_value(a.f[1], rs1, doc));
+    }
+    if (leader) {
+        const float ua = sa > 0.f ? __fmaf_rn(a.f[0].ka, sa, o0q) : 0.f;
+        const float ub = sb > 0.f ? __fmaf_rn(a.f[1].ka, sb, o1q) : 0.f;
+        emit_one_fused(a, __fadd_rn(ua, ub), (sa > 0.f ? 1u : 0u) | (sb > 0.f ? 2u : 0u), doc, thrq, (int)sq[s0 + qid].x,
+                       sfd + (s0 + qid) * 2);
+    }
+}
+
+// The chunk's queries, FOUR AT A TIME (8 lanes per query: lane = term position of both fields for the table
+// entries, = ladder step for the split): block-max skip, essential split, document-at-a-time evaluation.
+// Returns the mask of query slots that need the pass (or cannot be handled here: more than 8 terms in a
+// field, no threshold yet); the caller runs those one by one.
+__device__ __forceinline__ unsigned group_units(const FusedBlockArgs &a, const uint4 *sfd, const uint2 *sq, int nslots, int blk,
+                                                int doc_base, int lane, unsigned &skipped, unsigned &sparse_units,
+                                                unsigned &sparse_docs) {
+    const int qs = lane >> 3, tl = lane & 7, sh = qs * 8;
+    // ladder: row entries with >= 1, 2, 3, 5, 9, 17, 33 postings; step 7: every entry (the block-max test)
+    const int mycut = (tl == 0 || tl == 7) ? 1 : 1 + (1 << (tl - 1));
+    unsigned serial = 0u;
+    for (int s0 = 0; s0 < nslots; s0 += 4) {
+        const int sl = s0 + qs;
+        const bool qact = sl < nslots;
+        uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;
+        float thr_l = 0.f;
+        if (qact) {
+            d0 = sfd[sl * 2];
+            d1 = sfd[sl * 2 + 1];
+            thr_l = __uint_as_float(sq[sl].y);
+        }
+        const int m0 = (int)d0.y, m1 = (int)d1.y;
+        const bool ser = qact && (m0 > 8 || m1 > 8 || !(thr_l > 0.f));
+        const bool grp = qact && !ser;
+        const FTermEnt e0 = fused_load_entry(a.f[0], blk, (long long)d0.x + tl, grp && tl < m0);
+        const FTermEnt e1 = fused_load_entry(a.f[1], blk, (long long)d1.x + tl, grp && tl < m1);
+        const unsigned pb = __ballot_sync(0xFFFFFFFFu, e0.len > 0 || e1.len > 0);
+        const unsigned rb0 = __ballot_sync(0xFFFFFFFFu, e0.rslot >= 0), rb1 = __ballot_sync(0xFFFFFFFFu, e1.rslot >= 0);
+        const unsigned rm0 = tl == 7 ? 0xFFu : (rb0 >> sh) & 0xFFu;
+        const unsigned rm1 = tl == 7 ? 0xFFu : (rb1 >> sh) & 0xFFu;
+        const int mmax = min(8, (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(grp ? max(m0, m1) : 0)));
+        float b0 = 0.f, b1 = 0.f;
+        bool any0 = false, any1 = false;
+        for (int t = 0; t < mmax; t++) {
+            const int src = (lane & 24) | t;
+            const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, e0.pk, src), w1 = __shfl_sync(0xFFFFFFFFu, e1.pk, src);
+            if ((int)(w0 & kBlkLenMask) >= mycut && ((rm0 >> t) & 1u)) {
+                b0 = __fadd_rn(b0, __uint_as_float(w0 & ~kBlkLenMask));
+                any0 = true;
+            }
+            if ((int)(w1 & kBlkLenMask) >= mycut && ((rm1 >> t) & 1u)) {
+                b1 = __fadd_rn(b1, __uint_as_float(w1 & ~kBlkLenMask));
+                any1 = true;
+            }
+        }
+        const float o0 = __uint_as_float(d0.z), o1 = __uint_as_float(d1.z);
+        // the margins of the block-max test
+        const float f0 = any0 ? fminf(__fmul_rn(__fmaf_rn(a.f[0].ka, __fmul_rn(b0, 1.000004f), o0), 1.000002f), a.f[0].ucap) : 0.f;
+        const float f1 = any1 ? fminf(__fmul_rn(__fmaf_rn(a.f[1].ka, __fmul_rn(b1, 1.000004f), o1), 1.000002f), a.f[1].ucap) : 0.f;
+        const bool below = grp && __fmul_rn(__fadd_rn(f0, f1), 1.000002f) < thr_l;
+        const unsigned bm = (__ballot_sync(0xFFFFFFFFu, below) >> sh) & 0xFFu;
+        int L = 1;
+        if (bm & 0x7Fu) {
+            const int ci = __ffs(bm & 0x7Fu) - 1;
+            L = ci == 0 ? 1 : 1 + (1 << (ci - 1));
+        }
+        int n_e = ((e0.len > 0 && (e0.rslot < 0 || e0.len < L)) ? e0.len : 0) + ((e1.len > 0 && (e1.rslot < 0 || e1.len < L)) ? e1.len : 0);
+        n_e += __shfl_xor_sync(0xFFFFFFFFu, n_e, 1);
+        n_e += __shfl_xor_sync(0xFFFFFFFFu, n_e, 2);
+        n_e += __shfl_xor_sync(0xFFFFFFFFu, n_e, 4);
+        // 0 nothing to do, 1 skipped by the bound, 2 essential postings, 3 the pass
+        int cls;
+        if (!qact || (grp && !((pb >> sh) & 0xFFu))) cls = 0;
+        else if (ser) cls = 3;
+        else if (bm & 0x80u) cls = 1;
+        else if (!(bm & 0x7Fu) || n_e > kSparseMax) cls = 3;
+        else cls = n_e > 0 ? 2 : 1;
+        skipped += (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, cls == 1 && tl == 0));
+        const unsigned sb3 = __ballot_sync(0xFFFFFFFFu, cls == 3 && tl == 0);
+#pragma unroll
+        for (int gq = 0; gq < 4; gq++)
+            if ((sb3 >> (gq * 8)) & 1u) serial |= 1u << (s0 + gq);
+        unsigned pend = __ballot_sync(0xFFFFFFFFu, cls == 2 && tl == 0);
+        while (pend) {
+            unsigned batch = 0u;
+            int tot = 0;
+            for (unsigned pm = pend; pm; pm &= pm - 1) {
+                const int gl = __ffs(pm) - 1;
+                const int ne = __shfl_sync(0xFFFFFFFFu, n_e, gl);
+                if (tot + ne > kSparseMax) break;
+                tot += ne;
+                batch |= 0xFFu << gl;
+            }
+            pend &= ~batch;
+            sparse_round(a, e0, e1, cls == 2, L, thr_l, o0, o1, batch, mmax, s0, sfd, sq, doc_base, lane);
+            sparse_units += (unsigned)__popc(batch) >> 3;
+            sparse_docs += (unsigned)tot;
+        }
+    }
+    return serial;
 }
 
 // In FusedBlockArgs the fields are in TRAVERSAL order (cheapest index first): after each field but the last
@@ -552,7 +634,14 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
         }
         __syncwarp();
 
+        // two fields at pruning level >= 2: block-max skip and essential-posting evaluation four queries at a
+        // time; the loop below runs the queries that need the pass
+        unsigned serial = 0xFFFFFFFFu;
+        if (PAIR && F == 2 && !HAS_COS && a.prune >= 2 && a.sparse_mode)
+            serial = group_units(a, sfd, sq, nslots, blk, doc_base, lane, skipped, sparse_units, sparse_docs);
+
         for (int sidx = 0; sidx < nslots; sidx++) {
+            if (!((serial >> sidx) & 1u)) continue;
             const int q = (int)sq[sidx].x;
             const float thr = __uint_as_float(sq[sidx].y);
             const uint4 *sfd_q = sfd + sidx * F;
@@ -605,24 +694,6 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
                     dm[i] = __ballot_sync(0xFFFFFFFFu, e[i].dslot >= 0);
                     sm[i] = pres[i] & ~dm[i];
                 }
-                // essential-posting evaluation (see essential_split): only when every essential entry is an S entry
-                bool sparse = false;
-                int L = 0;
-                if (!HAS_COS && a.prune >= 2 && a.sparse_mode && thr > 0.f) {
-                    const FTermEnt &e1 = e[F > 1 ? 1 : 0];
-                    const int n_e = essential_split(a, e[0], e1, (int)sfd_q[0].y, (int)sfd_q[F > 1 ? 1 : 0].y, ofs[0], ofs[F > 1 ? 1 : 0],
-                                                    thr, lane, L);
-                    if (n_e >= 0 && n_e <= kSparseMax &&
-                        !__ballot_sync(0xFFFFFFFFu, (e[0].dslot >= 0 && e[0].len < L) || (e1.dslot >= 0 && e1.len < L))) {
-                        if (n_e == 0) {
-                            ne_skipped++;
-                            continue;
-                        }
-                        sparse = true;
-                        sparse_units++;
-                        sparse_docs += (unsigned)n_e;
-                    }
-                }
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     float *acc = i == 0 ? reinterpret_cast<float *>(U4) : B;
@@ -636,20 +707,6 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
                         fresh = false;
                         __syncwarp();
                     }
-                }
-                if (sparse) {
-                    sparse_walk(a, e[0], e[F > 1 ? 1 : 0], L, reinterpret_cast<float *>(U4), B, dm[0], dm[1], ofs[0], ofs[F > 1 ? 1 : 0],
-                                doc_base, lane, thr, q, sfd_q);
-                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 *A4z = reinterpret_cast<float4 *>(U4);
-                    if (sm[0])
-#pragma unroll
-                        for (int h = 0; h < kBlockDocs / 128; h++) A4z[h * 32 + lane] = zero4;
-                    if (sm[1])
-#pragma unroll
-                        for (int h = 0; h < kBlockDocs / 128; h++) B4[h * 32 + lane] = zero4;
-                    __syncwarp();
-                    continue;
                 }
                 // documents matching frequent (D) terms only: bounded by the D terms' block maxima in both fields
                 bool pred = false;
@@ -932,7 +989,7 @@ __device__ __forceinline__ void fused_select_one(const FusedSelectArgs &a, unsig
         if (i < a.c.n_fields && j < m_i[i]) {
             const longlong2 info = a.f[i].qt_info[2 * (t0_i[i] + j)];
             ip[i] = info.x;
-            slot[i] = (int)info.y;
+            slot[i] = (int)(info.y >> 32);  // any value row: hot or lookup
             trow[i] = a.f[i].qt_info[2 * (t0_i[i] + j) + 1];
             isdup[i] = a.f[i].q_nocount[t0_i[i] + j] != 0;
         }
@@ -961,7 +1018,7 @@ __device__ __forceinline__ void fused_select_one(const FusedSelectArgs &a, unsig
                 bool present = false;
                 if (act && j < m_i[i]) {
                     if (slot[i] >= 0) {
-                        val = ff.dense_vals[(size_t)slot[i] * (size_t)ff.dense_stride + doc];
+                        val = row_value(ff, slot[i], doc);
                         present = __float_as_uint(val) != 0x80000000u;
                     } else {
                         const uint2 ent = tab_lookup(ff.tab, trow[i], (int)(doc / (uint32_t)kBlockDocs));
@@ -1237,6 +1294,16 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         if (v >= 0 && v <= 6) n_rounds = v;
     }
 
+    int sparse_mode = 1;
+    if (const char *e = getenv("BB25_FUSED_SPARSE")) sparse_mode = atoi(e) != 0 ? 1 : 0;
+    if (n_fields == 2 && !has_cos && idx0->prune >= 2 && sparse_mode) {
+        // value rows of the mid-frequency terms for the essential-posting evaluation (built once per index)
+        for (int i = 0; i < n_fields; i++) {
+            std::lock_guard<std::mutex> lock(fields[i].index->mu);
+            if (ensure_lookup_rows(fields[i].index, st)) return 1;
+        }
+    }
+
     std::vector<int32_t> fb_list;
     std::vector<std::vector<int32_t>> h_terms((size_t)n_fields);
     std::vector<std::vector<int64_t>> h_qo((size_t)n_fields);
@@ -1312,6 +1379,8 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
             f.indptr = ix->indptr;
             f.tab = BlockTable{ix->tab_ent, ix->tab_bits, ix->tab_row};
             f.dense_vals = ix->dense_vals;
+            f.lookup_vals = ix->lookup_vals;
+            f.n_hot = ix->dense_vals ? ix->n_dense : 0;
             f.dense_stride = ix->dense_stride;
             f.doc_len = ix->doc_len;
             f.avgdl = ix->avgdl;
@@ -1407,8 +1476,7 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         ba.prune = idx0->prune;
         ba.pair_mode = n_fields == 2 ? 1 : 0;
         if (const char *e = getenv("BB25_FUSED_PAIR")) ba.pair_mode = (n_fields == 2 && atoi(e) != 0) ? 1 : 0;
-        ba.sparse_mode = 1;
-        if (const char *e = getenv("BB25_FUSED_SPARSE")) ba.sparse_mode = atoi(e) != 0 ? 1 : 0;
+        ba.sparse_mode = sparse_mode;
         ba.work_counter = d_work;
         ba.stats = d_stats;
         float trav_ms = 0.f;

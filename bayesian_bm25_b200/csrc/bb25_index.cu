@@ -304,6 +304,73 @@ int ensure_tile_table(bb25_index *idx, cudaStream_t st) {
     return 0;
 }
 
+// Lookup rows (see bb25_index::lookup_vals): built once, on the first call that can use them.  Terms with
+// df >= n_docs / DIV that have no hot row, most frequent first, as many as fit the budget: at most
+// BB25_LOOKUP_MAX_GB (default: 45 % of the free device memory, leaving 6 GB).  BB25_LOOKUP_DIV=0: none.
+// Failing to allocate is not an error: row_slot then equals dense_slot and callers take their other paths.
+int ensure_lookup_rows(bb25_index *idx, cudaStream_t st) {
+    if (idx->lookup_tried) return 0;
+    idx->lookup_tried = true;
+    const int64_t n_vocab = idx->n_vocab;
+    std::vector<int32_t> h_slot((size_t)n_vocab, -1);
+    if (idx->dense_slot)
+        BB25_CUDA(cudaMemcpy(h_slot.data(), idx->dense_slot, (size_t)n_vocab * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (!idx->dense_vals) std::fill(h_slot.begin(), h_slot.end(), -1);
+    int div = 64;
+    if (const char *e = getenv("BB25_LOOKUP_DIV")) div = atoi(e);
+    std::vector<int32_t> h_terms;
+    if (div > 0 && idx->dense_stride > 0) {
+        std::vector<int64_t> h_indptr((size_t)n_vocab + 1);
+        BB25_CUDA(cudaMemcpy(h_indptr.data(), idx->indptr, h_indptr.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        std::vector<std::pair<int64_t, int32_t>> cand;
+        for (int64_t t = 0; t < n_vocab; t++) {
+            const int64_t df = h_indptr[t + 1] - h_indptr[t];
+            if (df > 0 && h_slot[t] < 0 && df * (int64_t)div >= idx->n_docs) cand.emplace_back(-df, (int32_t)t);
+        }
+        std::sort(cand.begin(), cand.end());
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        double budget = 0.45 * (double)free_b;
+        if ((double)free_b - budget < 6e9) budget = (double)free_b - 6e9;
+        if (const char *e = getenv("BB25_LOOKUP_MAX_GB")) budget = std::min(budget, atof(e) * 1e9);
+        const double row_b = (double)idx->dense_stride * sizeof(float);
+        size_t n_rows = budget > 0 ? (size_t)(budget / row_b) : 0;
+        n_rows = std::min(n_rows, std::min(cand.size(), (size_t)32768));
+        if (n_rows > 0) {
+            const size_t nb = n_rows * (size_t)idx->dense_stride * sizeof(float);
+            if (cudaMalloc(&idx->lookup_vals, nb) != cudaSuccess) {
+                cudaGetLastError();
+                idx->lookup_vals = nullptr;
+                n_rows = 0;
+            } else {
+                for (size_t i = 0; i < n_rows; i++) {
+                    h_slot[cand[i].second] = idx->n_dense + (int32_t)i;
+                    h_terms.push_back(cand[i].second);
+                }
+                fill_u32_kernel<<<(unsigned)((nb / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<unsigned int *>(idx->lookup_vals), nb / 4,
+                                                                                 0x80000000u);
+                int32_t *d_terms = nullptr;
+                BB25_CUDA(cudaMalloc(&d_terms, h_terms.size() * sizeof(int32_t)));
+                BB25_CUDA(cudaMemcpyAsync(d_terms, h_terms.data(), h_terms.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                dim3 grid(32, (unsigned)n_rows);
+                build_dense_rows_kernel<<<grid, 256, 0, st>>>(idx->data, idx->indices, idx->indptr, d_terms, idx->dense_stride,
+                                                             idx->lookup_vals);
+                count_launch(2);
+                BB25_CUDA(cudaGetLastError());
+                BB25_CUDA(cudaStreamSynchronize(st));
+                cudaFree(d_terms);
+                idx->device_bytes += nb;
+            }
+        }
+        idx->n_lookup = (int)n_rows;
+    }
+    BB25_CUDA(cudaMalloc(&idx->row_slot, (size_t)std::max<int64_t>(n_vocab, 1) * sizeof(int32_t)));
+    BB25_CUDA(cudaMemcpyAsync(idx->row_slot, h_slot.data(), (size_t)n_vocab * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    BB25_CUDA(cudaStreamSynchronize(st));
+    idx->device_bytes += (size_t)n_vocab * sizeof(int32_t);
+    return 0;
+}
+
 int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out) {
     auto it = idx->kth_cache.find(k);
     if (it != idx->kth_cache.end()) {
@@ -571,6 +638,8 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->dense_slot);
     cudaFree(idx->dense_vals);
     cudaFree(idx->dense_h);
+    cudaFree(idx->lookup_vals);
+    cudaFree(idx->row_slot);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
     if (idx->ws) cudaFree(idx->ws);
     if (idx->hs_dev) cudaFree(idx->hs_dev);

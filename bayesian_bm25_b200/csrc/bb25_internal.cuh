@@ -248,6 +248,15 @@ struct bb25_index {
     __half *dense_h = nullptr;      // the same rows as fp16 UPPER BOUNDS (rounded up, absent = 0): order-free pass only
     int n_dense = 0;
     int64_t dense_stride = 0;       // n_blocks * kBlockDocs
+    // LOOKUP rows (built on the first fused batch that can use them, ensure_lookup_rows): the same fp32 value
+    // rows for the mid-frequency terms (df >= n_docs / BB25_LOOKUP_DIV, within a memory budget).  No traversal
+    // pass streams them; they make "value of term t in document d" one 4-byte load where a document is
+    // evaluated on its own (essential-posting evaluation of the fused batch, exact evaluation of candidates).
+    // row_slot[t]: the hot slot (< n_dense), n_dense + lookup row, or -1.
+    float *lookup_vals = nullptr;   // [n_lookup][dense_stride]
+    int32_t *row_slot = nullptr;    // [n_vocab]
+    int n_lookup = 0;
+    bool lookup_tried = false;
     std::map<int, float *> kth_cache;  // k -> fp32[n_vocab] k-th largest posting value per term
     // grow-only device workspace shared by query calls (serialised by mu)
     std::mutex mu;
@@ -303,4 +312,5 @@ int prep_queries_launch(const bb25_index *idx, const int32_t *q_terms, const int
                         longlong2 *qt_info, int *err, cudaStream_t st);
 int get_kth_values(bb25_index *idx, int k, cudaStream_t st, const float **out);
 int ensure_tile_table(bb25_index *idx, cudaStream_t st);
+int ensure_lookup_rows(bb25_index *idx, cudaStream_t st);
 }  // namespace bb25

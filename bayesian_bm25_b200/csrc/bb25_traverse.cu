@@ -279,7 +279,8 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
                                     int *err, const int64_t *__restrict__ indptr = nullptr,
                                     const int32_t *__restrict__ dense_slot = nullptr,
                                     const longlong2 *__restrict__ tab_row = nullptr,
-                                    longlong2 *__restrict__ qt_info = nullptr) {
+                                    longlong2 *__restrict__ qt_info = nullptr,
+                                    const int32_t *__restrict__ row_slot = nullptr) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_q) return;
     // Offsets are rebased to the batch's first term and clamped into [0, n_terms_total]: whatever
@@ -306,7 +307,10 @@ __global__ void prep_queries_kernel(const int32_t *__restrict__ q_terms, const i
         // per query term: posting-list start and dense-row slot, so that the traversal reads them
         // alongside the term id instead of after it
         if (qt_info) {
-            qt_info[2 * i] = make_longlong2(indptr[t], dense_slot ? (long long)dense_slot[t] : -1ll);
+            // .y: low half = hot (dense) slot, high half = slot of any value row (hot or lookup), -1 = none
+            const int hot = dense_slot ? dense_slot[t] : -1;
+            const int any = row_slot ? row_slot[t] : hot;
+            qt_info[2 * i] = make_longlong2(indptr[t], (long long)(((unsigned long long)(uint32_t)any << 32) | (unsigned long long)(uint32_t)hot));
             qt_info[2 * i + 1] = tab_row[t];
         }
         if (kth) {
@@ -328,7 +332,8 @@ int prep_queries_launch(const bb25_index *idx, const int32_t *q_terms, const int
                         longlong2 *qt_info, int *err, cudaStream_t st) {
     prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(
         q_terms, q_off, n_q, term_base, n_terms_total, idx->n_vocab, nullptr, qt_ws, nocount, qo_ws, nullptr, nullptr,
-        nullptr, err, idx->indptr, idx->dense_vals ? idx->dense_slot : nullptr, idx->tab_row, qt_info);
+        nullptr, err, idx->indptr, idx->dense_vals ? idx->dense_slot : nullptr, idx->tab_row, qt_info,
+        idx->lookup_vals ? idx->row_slot : nullptr);
     BB25_LAUNCH_CHECK();
     return 0;
 }
