@@ -79,6 +79,7 @@ SIGNATURES = {
     "bb25_index_set_pruning": (_i32, [_vp, _i32]),
     "bb25_retrieve_prune_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "bb25_retrieve_route_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "bb25_retrieve_sparse_units": (_i32, [_vp, C.POINTER(_i64)]),
     "bb25_retrieve_timing": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "bb25_merge_topk": (_i32, [_i32, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "bb25_pack_topk": (_i32, [_i32, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -267,7 +267,7 @@ struct bb25_index {
     // stats of the last retrieve_batch
     int64_t st_launches = 0, st_passes = 0, st_reruns = 0, st_candidates = 0;
     int64_t st_routed = 0, st_cand_items = 0;  // queries evaluated candidate-by-candidate / their work items
-    int64_t st_units = 0, st_units_skipped = 0, st_units_maxscore = 0;  // (block, query) units visited / pruned / evaluated with the level-2 restriction
+    int64_t st_units = 0, st_units_skipped = 0, st_units_maxscore = 0, st_units_sparse = 0;  // (block, query) units visited / pruned / evaluated with the level-2 restriction
     // CUDA-event pairs around the traversal launches of the last retrieve_batch
     static constexpr int kMaxEv = 256;
     cudaEvent_t ev[2 * kMaxEv] = {};

@@ -793,8 +793,12 @@ struct BlockArgs {
     const float *dense_vals;
     const __half *dense_h;  // fp16 upper-bound copy of the dense rows (order-free pass only) or NULL
     int64_t dense_stride;
+    const float *lookup_vals;  // value rows of the mid-frequency terms (bb25_index::lookup_vals) or NULL
+    int n_hot;                 // row slots below this are rows of dense_vals, the others rows of lookup_vals
+    int sparse_mode;           // pruning level >= 2: units evaluated through their essential postings (group_units)
     unsigned long long *work_counter;
-    unsigned long long *stats;  // [0] (block, query) units handed out, [1] units pruned by the block-max bound, [2] units under the level-2 restriction
+    unsigned long long *stats;  // [0] (block, query) units handed out, [1] units pruned by the block-max bound, [2] units under
+                                // the level-2 restriction, [3] units evaluated through their essential postings
 };
 
 // per-warp shared memory: 1024 fp32 accumulators
@@ -861,6 +865,31 @@ struct TermEnt {
     float bmax;
     int dslot;  // dense value row of the term (-1: none, or no posting in this block)
 };
+// the same with the slot of ANY value row (hot or lookup) and the packed table word, for group_units
+struct TermEntX {
+    long long start;
+    int len;
+    int rslot;
+    uint32_t pk;  // block maximum (upper 21 bits, rounded up) | slice length
+};
+template <bool SPARSE_TAB>
+__device__ __forceinline__ TermEntX load_term_entry_x(const BlockArgs &a, int blk, long long pos, bool active) {
+    TermEntX e;
+    e.start = 0;
+    e.len = 0;
+    e.rslot = -1;
+    e.pk = 0u;
+    if (active) {
+        const longlong2 info = a.qt_info[2 * pos];       // (indptr[t], hot slot | any-row slot << 32)
+        const longlong2 trow = a.qt_info[2 * pos + 1];   // the term's block-table row
+        const uint2 ent = SPARSE_TAB ? tab_lookup(a.tab, trow, blk) : a.tab.ent[trow.x + blk];
+        e.pk = ent.y;
+        e.len = (int)(ent.y & kBlkLenMask);
+        e.start = info.x + (long long)ent.x;
+        e.rslot = e.len > 0 ? (int)(info.y >> 32) : -1;
+    }
+    return e;
+}
 
 template <bool SPARSE_TAB>
 __device__ __forceinline__ TermEnt load_term_entry(const BlockArgs &a, int blk, long long pos, bool active) {
@@ -1002,6 +1031,146 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Essential-posting evaluation of units (pruning level >= 2, order-free kernel): MaxScore -- the partition
+// behind wand_upper_bound (probability.py:205-236) and BlockMaxIndex (scorer.py:33-142) -- at the
+// granularity of one 1024-document block, FOUR queries of the chunk at a time (8 lanes per query).
+//
+// A unit's terms are split: NON-ESSENTIAL = the terms that have a value row (hot or lookup) and at least L
+// postings in this block, for the smallest L of a fixed ladder whose summed block maxima (query order,
+// exactly the block-max test restricted to the subset) stay below the query's threshold.  A document that
+// matches non-essential terms only cannot reach the threshold, so every qualifying document has a posting
+// in an ESSENTIAL slice (row-less terms; row terms with fewer than L postings here).  When the unit's
+// essential slices hold at most 32 postings it is evaluated document-at-a-time in one round: lane =
+// essential posting (doc id and value straight from the slice), postings of one document are combined
+// with a warp match, every non-essential term's value is ONE 4-byte load from its row.  No accumulators,
+// no scatter, no pass over 1024 documents.  The candidates carry any-order sums; select_kernel re-scores
+// them exactly, as it does for the order-free pass.  The ladder's last step is the full term set = the
+// block-max skip test.  Returns the query slots that need the pass (or cannot be handled here).
+// ---------------------------------------------------------------------------------
+constexpr int kSparseMax = 32;
+
+__device__ __forceinline__ float row_value(const BlockArgs &a, int rslot, uint32_t doc) {
+    return rslot < a.n_hot ? a.dense_vals[(size_t)rslot * (size_t)a.dense_stride + doc]
+                           : a.lookup_vals[(size_t)(rslot - a.n_hot) * (size_t)a.dense_stride + doc];  // absent: -0.0f
+}
+
+template <bool SPARSE_TAB>
+__device__ __forceinline__ unsigned group_units(const BlockArgs &a, const uint4 *sdesc, int nslots, int blk, int doc_base,
+                                                int lane, unsigned int *scnt) {
+    const int qs = lane >> 3, tl = lane & 7, sh = qs * 8;
+    // ladder: row terms with >= 1, 2, 3, 5, 9, 17, 33 postings here; step 7: every term (the block-max test)
+    const int mycut = (tl == 0 || tl == 7) ? 1 : 1 + (1 << (tl - 1));
+    unsigned serial = 0u;
+    for (int s0 = 0; s0 < nslots; s0 += 4) {
+        const int sl = s0 + qs;
+        const bool qact = sl < nslots;
+        const uint4 d = qact ? sdesc[sl] : make_uint4(0u, 0u, 0u, 0u);  // q, term count, first term position, threshold score bits
+        const int m = (int)d.y;
+        const uint32_t thr_score = d.w;
+        const bool ser = qact && (m > 8 || thr_score == 0u);
+        const bool grp = qact && !ser && m > 0;
+        const TermEntX e = load_term_entry_x<SPARSE_TAB>(a, blk, (long long)(int)d.z + tl, grp && tl < m);
+        const unsigned pb = __ballot_sync(0xFFFFFFFFu, e.len > 0);
+        const unsigned rb = __ballot_sync(0xFFFFFFFFu, e.rslot >= 0);
+        const unsigned rm = tl == 7 ? 0xFFu : (rb >> sh) & 0xFFu;
+        const int mmax = min(8, (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(grp ? m : 0)));
+        float ub = 0.f;
+        for (int t = 0; t < mmax; t++) {
+            const uint32_t w = __shfl_sync(0xFFFFFFFFu, e.pk, (lane & 24) | t);
+            if ((int)(w & kBlkLenMask) >= mycut && ((rm >> t) & 1u)) ub = __fadd_rn(ub, __uint_as_float(w & ~kBlkLenMask));
+        }
+        const bool below = grp && __float_as_uint(ub) < thr_score;
+        const unsigned bm = (__ballot_sync(0xFFFFFFFFu, below) >> sh) & 0xFFu;
+        int L = 1;
+        if (bm & 0x7Fu) {
+            const int ci = __ffs(bm & 0x7Fu) - 1;
+            L = ci == 0 ? 1 : 1 + (1 << (ci - 1));
+        }
+        const bool ess = e.len > 0 && (e.rslot < 0 || e.len < L);
+        int n_e = ess ? e.len : 0;
+        n_e += __shfl_xor_sync(0xFFFFFFFFu, n_e, 1);
+        n_e += __shfl_xor_sync(0xFFFFFFFFu, n_e, 2);
+        n_e += __shfl_xor_sync(0xFFFFFFFFu, n_e, 4);
+        // 0 nothing to do, 1 skipped by the bound, 2 essential postings, 3 the pass
+        int cls;
+        if (!qact || (!ser && !((pb >> sh) & 0xFFu))) cls = 0;
+        else if (ser) cls = 3;
+        else if (bm & 0x80u) cls = 1;
+        else if (!(bm & 0x7Fu) || n_e > kSparseMax) cls = 3;
+        else cls = n_e > 0 ? 2 : 1;
+        const unsigned n_skip = (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, cls == 1 && tl == 0));
+        const unsigned sb3 = __ballot_sync(0xFFFFFFFFu, cls == 3 && tl == 0);
+#pragma unroll
+        for (int gq = 0; gq < 4; gq++)
+            if ((sb3 >> (gq * 8)) & 1u) serial |= 1u << (s0 + gq);
+        unsigned pend = __ballot_sync(0xFFFFFFFFu, cls == 2 && tl == 0);
+        if (lane == 0) {
+            scnt[0] += n_skip;
+            scnt[2] += (unsigned)__popc(pend);
+        }
+        while (pend) {
+            unsigned batch = 0u;
+            int tot = 0;
+            for (unsigned pm = pend; pm; pm &= pm - 1) {
+                const int gl = __ffs(pm) - 1;
+                const int ne = __shfl_sync(0xFFFFFFFFu, n_e, gl);
+                if (tot + ne > kSparseMax) break;
+                tot += ne;
+                batch |= 0xFFu << gl;
+            }
+            pend &= ~batch;
+            // ---- one round: lane = essential posting of one of the batch's queries ----
+            int o = -1, qid = 0, fill = 0;
+            float v = 0.f;
+            for (unsigned mm = __ballot_sync(0xFFFFFFFFu, cls == 2 && ess) & batch; mm; mm &= mm - 1) {
+                const int src = __ffs(mm) - 1;
+                const int len = __shfl_sync(0xFFFFFFFFu, e.len, src);
+                const long long s = shfl_ll(e.start, src);
+                const int r = lane - fill;
+                if (r >= 0 && r < len) {
+                    o = ld_nc_s32(a.indices + s + r) - doc_base;
+                    v = ld_nc_f32(a.data + s + r);
+                    qid = src >> 3;
+                }
+                fill += len;
+            }
+            const bool valid = o >= 0;
+            // postings of one (query, document) -- several essential slices may hold it -- are summed by the first lane
+            const unsigned g = __match_any_sync(0xFFFFFFFFu, valid ? ((qid << 10) | o) : (0x10000 | lane));
+            const int rounds = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)__popc(g));
+            float sum = 0.f;
+            unsigned rem = g;
+            for (int r = 0; r < rounds; r++) {
+                const float vv = __shfl_sync(0xFFFFFFFFu, v, rem ? __ffs(rem) - 1 : lane);
+                if (rem) {
+                    sum = __fadd_rn(sum, vv);
+                    rem &= rem - 1;
+                }
+            }
+            const bool leader = valid && (__ffs(g) - 1 == lane);
+            const uint32_t doc = (uint32_t)(doc_base + (valid ? o : 0));
+            const int ql = qid << 3;  // first lane of the posting's query
+            const int Lq = __shfl_sync(0xFFFFFFFFu, L, ql);
+            const uint32_t thrq = __shfl_sync(0xFFFFFFFFu, thr_score, ql);
+            const int qq = __shfl_sync(0xFFFFFFFFu, (int)d.x, ql);
+            for (int t = 0; t < mmax; t++) {
+                const int rs = __shfl_sync(0xFFFFFFFFu, e.rslot, ql | t), ln = __shfl_sync(0xFFFFFFFFu, e.len, ql | t);
+                if (leader && rs >= 0 && ln >= Lq) sum = __fadd_rn(sum, row_value(a, rs, doc));
+            }
+            if (leader) {
+                const uint32_t thr_rel = __float_as_uint(__fmul_rn(__uint_as_float(thrq), 0.99999f));
+                const uint32_t bits = __float_as_uint(sum);
+                if (sum > 0.f && bits >= thr_rel) {
+                    const unsigned int pos = atomicAdd(a.cand_cnt + qq, 1u);
+                    if (pos < (unsigned)a.cap) a.cand_key[(size_t)qq * (size_t)a.cap + pos] = make_key(bits, doc, 0u);
+                }
+            }
+        }
+    }
+    return serial;
+}
+
 // Resident CTAs per SM (= register cap) of the order-free kernel, measured on config 2: the exhaustive
 // pass likes 5 x 8 warps at 48 registers (61.0 vs 62.5 ms per step), the pruned passes, whose units are
 // fewer and heavier, 4 x 8 warps at 64 registers (39.7 vs 40.7 ms).  The query-order kernel runs 6.
@@ -1011,7 +1180,7 @@ __device__ __forceinline__ void order_free_pass(const BlockArgs &a, const PassAr
 #ifndef BB25_BLOCK_CTAS_PRUNED
 #define BB25_BLOCK_CTAS_PRUNED 4
 #endif
-template <int WARPS, bool EXACT, bool SPARSE_TAB, int CTAS, bool HALF>
+template <int WARPS, bool EXACT, bool SPARSE_TAB, int CTAS, bool HALF, bool GROUP = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_constant__ BlockArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
@@ -1055,7 +1224,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
         }
         __syncwarp();
 
+        // pruning level >= 2: block-max skip and essential-posting evaluation four queries at a time; the loop
+        // below runs the queries that need the pass
+        unsigned serial = 0xFFFFFFFFu;
+        if (GROUP && !EXACT && a.sparse_mode) serial = group_units<SPARSE_TAB>(a, sdesc, nslots, blk, doc_base, lane, scnt);
+
         for (int sidx = 0; sidx < nslots; sidx++) {
+            if (GROUP && !((serial >> sidx) & 1u)) continue;
             const uint4 desc = sdesc[sidx];
             const int m = (int)desc.y;
             if (m == 0) continue;
@@ -1234,6 +1409,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
     if (lane == 0 && a.stats) {
         atomicAdd(&a.stats[1], (unsigned long long)scnt[0]);
         atomicAdd(&a.stats[2], (unsigned long long)scnt[1]);
+        if (GROUP && scnt[2]) atomicAdd(&a.stats[3], (unsigned long long)scnt[2]);
     }
 }
 
@@ -1253,16 +1429,20 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
     const bool sparse_tab = idx->tab_sparse_terms > 0;
-#define BB25_LAUNCH_BLOCK(EX, SP, CT, HF)                                                                             \
+#define BB25_LAUNCH_BLOCK_G(EX, SP, CT, HF, GR)                                                                       \
     do {                                                                                                              \
-        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP, CT, HF>,                                        \
+        BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP, CT, HF, GR>,                                    \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
-        block_kernel<BK_WARPS, EX, SP, CT, HF><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                       \
+        block_kernel<BK_WARPS, EX, SP, CT, HF, GR><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                   \
     } while (0)
+#define BB25_LAUNCH_BLOCK(EX, SP, CT, HF) BB25_LAUNCH_BLOCK_G(EX, SP, CT, HF, false)
     const bool half_rows = !exact && a.dense_h != nullptr;
     if (exact) {
         if (sparse_tab) BB25_LAUNCH_BLOCK(true, true, 6, false);
         else BB25_LAUNCH_BLOCK(true, false, 6, false);
+    } else if (pruned_cfg && a.sparse_mode) {
+        if (sparse_tab) { if (half_rows) BB25_LAUNCH_BLOCK_G(false, true, BB25_BLOCK_CTAS_PRUNED, true, true); else BB25_LAUNCH_BLOCK_G(false, true, BB25_BLOCK_CTAS_PRUNED, false, true); }
+        else { if (half_rows) BB25_LAUNCH_BLOCK_G(false, false, BB25_BLOCK_CTAS_PRUNED, true, true); else BB25_LAUNCH_BLOCK_G(false, false, BB25_BLOCK_CTAS_PRUNED, false, true); }
     } else if (pruned_cfg) {
         if (sparse_tab) { if (half_rows) BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS_PRUNED, true); else BB25_LAUNCH_BLOCK(false, true, BB25_BLOCK_CTAS_PRUNED, false); }
         else { if (half_rows) BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS_PRUNED, true); else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS_PRUNED, false); }
@@ -1271,6 +1451,7 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
         else { if (half_rows) BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS, true); else BB25_LAUNCH_BLOCK(false, false, BB25_BLOCK_CTAS, false); }
     }
 #undef BB25_LAUNCH_BLOCK
+#undef BB25_LAUNCH_BLOCK_G
     BB25_LAUNCH_CHECK();
     return 0;
 }
@@ -1788,7 +1969,7 @@ __global__ void compact_bad_kernel(const uint8_t *__restrict__ bad, int64_t n_q,
 
 // what the host reads back, once, at the end of a batch
 struct BatchReport {
-    unsigned long long n_cand, units, units_skipped, units_maxscore;
+    unsigned long long n_cand, units, units_skipped, units_maxscore, units_sparse;
     unsigned int route[4];  // queries on the candidate path, on the block path, candidate work items (first round), -
     unsigned int n_bad;
     int err;
@@ -1804,6 +1985,7 @@ __global__ void report_kernel(const unsigned long long *__restrict__ n_cand, con
     r.units = stats[0];
     r.units_skipped = stats[1];
     r.units_maxscore = stats[2];
+    r.units_sparse = stats[3];
     r.route[0] = route[0];
     r.route[1] = route[1];
     r.route[2] = route[3];  // first-round work items (route[2] is reused by the repair rounds)
@@ -1834,6 +2016,13 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     // round trip: list lengths and overflow counts stay on the device, every stage is followed by
     // a fixed number of repair rounds (kernels that find an empty list leave at once), and ONE
     // synchronisation at the end reads the report.
+    int sparse_mode = idx->prune >= 2 && use_block_kernel() ? 1 : 0;
+    if (const char *e = getenv("BB25_SPARSE")) sparse_mode = sparse_mode && atoi(e) != 0;
+    if (sparse_mode) {
+        // value rows of the mid-frequency terms for the essential-posting evaluation (built once per index)
+        if (ensure_lookup_rows(idx, st)) return 1;
+        if (!idx->lookup_vals && !idx->dense_vals) sparse_mode = 0;
+    }
     int cap = 1024;
     while (cap < 8 * k && cap < 16384) cap <<= 1;
     int n_rounds = 3;  // repair rounds enqueued after every stage
@@ -1884,7 +2073,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     unsigned long long *d_work = (unsigned long long *)(ws + o_ctr);
     int *d_err = (int *)(ws + o_ctr + 16);
     unsigned long long *d_ncand = (unsigned long long *)(ws + o_ctr + 24);
-    unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [3]
+    unsigned long long *d_stats = (unsigned long long *)(ws + o_ctr + 32);  // [4]
     unsigned int *d_route = (unsigned int *)(ws + o_ctr + 64);  // [0] n_a, [1] n_b, [2] n_items, [3] n_items of the first round
     unsigned int *d_nbad = (unsigned int *)(ws + o_ctr + 80);
     unsigned int *d_round = (unsigned int *)(ws + o_ctr + 128);  // overflow counts: [stage][round], stage 0 = candidate path
@@ -1912,7 +2101,8 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
                                                                       idx->n_vocab, kth, d_terms, d_nc, d_qo, d_thr, d_cnt,
                                                                       d_prev, d_err, idx->indptr,
                                                                       idx->dense_vals ? idx->dense_slot : nullptr,
-                                                                      idx->tab_row, (longlong2 *)(ws + o_info));
+                                                                      idx->tab_row, (longlong2 *)(ws + o_info),
+                                                                      idx->lookup_vals ? idx->row_slot : nullptr);
     BB25_LAUNCH_CHECK();
 
     // tile groups: a small first group makes a loose threshold seed cheap to repair,
@@ -1978,6 +2168,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
         if (atoi(e) == 0) ba.dense_h = nullptr;
     }
     ba.dense_stride = idx->dense_stride;
+    ba.lookup_vals = idx->lookup_vals;
+    ba.n_hot = idx->dense_vals ? idx->n_dense : 0;
+    ba.sparse_mode = sparse_mode;
     ba.work_counter = d_work;
     ba.stats = d_stats;
 
@@ -2192,6 +2385,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     idx->st_units = (int64_t)h_rep->units;
     idx->st_units_skipped = (int64_t)h_rep->units_skipped;
     idx->st_units_maxscore = (int64_t)h_rep->units_maxscore;
+    idx->st_units_sparse = (int64_t)h_rep->units_sparse;
     idx->st_routed = (int64_t)h_rep->route[0];
     idx->st_cand_items = (int64_t)h_rep->route[2];
     idx->st_reruns = (int64_t)h_rep->reruns;
@@ -2491,6 +2685,12 @@ int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *un
     if (units) *units = idx->st_units;
     if (units_skipped) *units_skipped = idx->st_units_skipped;
     if (units_maxscore) *units_maxscore = idx->st_units_maxscore;
+    return 0;
+}
+
+int bb25_retrieve_sparse_units(const bb25_index *idx, int64_t *units_sparse) {
+    if (!idx) { set_error("index is NULL"); return 1; }
+    if (units_sparse) *units_sparse = idx->st_units_sparse;
     return 0;
 }
 

@@ -529,6 +529,9 @@ class BayesianBM25Scorer:
         rq, wi = C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().bb25_retrieve_route_stats(self._handle, C.byref(rq), C.byref(wi)))
         out["routed_queries"], out["candidate_items"] = rq.value, wi.value
+        us = C.c_int64()
+        _lib.check(_lib.lib().bb25_retrieve_sparse_units(self._handle, C.byref(us)))
+        out["units_sparse"] = us.value
         sy, bad, dn = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().bb25_retrieve_sync_stats(self._handle, C.byref(sy), C.byref(bad), C.byref(dn)))
         out["host_syncs"], out["repaired_queries"], out["dense_fallback_queries"] = sy.value, bad.value, dn.value

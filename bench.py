@@ -436,7 +436,7 @@ def main():
         launches0 = _lib.lib().bb25_launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {"traverse_ms": 0.0, "traverse_launches": 0, "rerun_queries": 0, "units": 0, "units_skipped": 0,
-               "units_maxscore": 0, "routed_queries": 0, "candidate_items": 0, "host_syncs": 0,
+               "units_maxscore": 0, "units_sparse": 0, "routed_queries": 0, "candidate_items": 0, "host_syncs": 0,
                "repaired_queries": 0, "dense_fallback_queries": 0}
         barrier()
         ev0.record()
@@ -566,6 +566,7 @@ def main():
                 "e2e_retrieve_ids_value": args.queries * args.steps / pr["e2e_ids_s"], "results_identical": same,
                 "block_docs": 1024, "units_per_step": pr["units"], "units_skipped_per_step": pr["units_skipped"],
                 "units_maxscore_per_step": pr["units_maxscore"],
+                "units_by_essential_postings_per_step": pr["units_sparse"],
                 "queries_routed_to_candidate_path_per_step": pr["routed_queries"],
                 "candidate_items_per_step": pr["candidate_items"], "host_syncs_per_step": pr["host_syncs"],
             },

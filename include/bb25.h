@@ -222,6 +222,11 @@ int bb25_index_set_pruning(bb25_index *idx, int level);
 int bb25_retrieve_prune_stats(const bb25_index *idx, int64_t *units, int64_t *units_skipped,
                               int64_t *units_maxscore);
 int bb25_retrieve_route_stats(const bb25_index *idx, int64_t *routed_queries, int64_t *work_items);
+/* Levels >= 2 also evaluate (block, query) units through their ESSENTIAL postings (MaxScore's split per
+ * 1024-document block: the terms with a value row and many postings in the block whose summed block
+ * maxima stay below the threshold are non-essential; the <= 32 documents of the other slices are
+ * evaluated one by one, non-essential values read from the rows).  Units handled that way in the last batch: */
+int bb25_retrieve_sparse_units(const bb25_index *idx, int64_t *units_sparse);
 
 /* Device time of the traversal kernel in the last bb25_retrieve_batch on this handle,
  * measured with CUDA events on the call's stream around every traversal launch

@@ -269,3 +269,38 @@ def test_config5_full_size_50m_docs():
             want = _oracle_fused(mf, hosts, params, [qs[q], qs[q]])
             np.testing.assert_allclose(fused[lo:hi].cpu().numpy(), want, rtol=1e-9, atol=1e-18)
         del fused
+
+
+@pytest.mark.parametrize("lookup_div", ["64", "0", "100000"])
+def test_essential_posting_evaluation_of_the_fused_key(lookup_div, monkeypatch):
+    """Two fields, pruning level >= 2: units are evaluated four queries at a time through their essential
+    postings (MaxScore split per block on the fused key; non-essential values from the hot / lookup rows).
+    Default lookup rows, none (BB25_LOOKUP_DIV=0), rows for every term, and the evaluation switched off
+    (BB25_FUSED_SPARSE=0) all return the exhaustive result, which is checked against the oracle; queries with
+    9..30 terms (evaluated one by one), duplicates, rare-only and frequent-only queries included."""
+    monkeypatch.setenv("BB25_LOOKUP_DIV", lookup_div)
+    vocab = 6000
+    mf, hosts, params = _two_field(200_000, vocab, seed=211, title_len=7.0, body_len=45.0)
+    rng = np.random.default_rng(5)
+    extra = [[5999], [5998, 5997], [0, 1, 2], [0, 0, 3000, 3000], rng.integers(0, vocab, 10), rng.integers(0, vocab, 20),
+             rng.integers(0, vocab, 30), rng.integers(0, 40, 9), rng.integers(2500, vocab, 8), [3, 4500]]
+    qs = _queries(150, vocab, 9, extra)
+    fq = [_flat(qs), _flat(qs)]
+    mf.set_pruning(0)
+    want = {k: mf.retrieve_ids_batch(fq, k) for k in (10, 100)}
+    from oracle import coracle
+    for q in (0, 1, 2, 150, 153, 154, 159):  # the exhaustive result against the oracle
+        w_ids, w_vals = coracle.topk_f64(_oracle_fused(mf, hosts, params, [qs[q], qs[q]]), 10)
+        np.testing.assert_array_equal(want[10][0][q], w_ids, err_msg=f"query {q}")
+        np.testing.assert_allclose(want[10][1][q], w_vals, rtol=1e-9, atol=1e-18)
+    stats = {}
+    for level in (2, 3):
+        for sparse in ("1", "0"):
+            monkeypatch.setenv("BB25_FUSED_SPARSE", sparse)
+            mf.set_pruning(level)
+            for k in (10, 100):
+                ids, vals = mf.retrieve_ids_batch(fq, k)
+                np.testing.assert_array_equal(ids, want[k][0], err_msg=f"level {level} sparse {sparse} k {k}")
+                np.testing.assert_array_equal(vals, want[k][1], err_msg=f"level {level} sparse {sparse} k {k}")
+            stats[(level, sparse)] = mf.stats()
+    assert stats[(3, "1")]["units_sparse"] > 0 and stats[(3, "0")]["units_sparse"] == 0

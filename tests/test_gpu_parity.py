@@ -583,3 +583,44 @@ def test_full_size_config2_properties():
     np.testing.assert_array_equal(m_ids.cpu().numpy(), ids)
     np.testing.assert_array_equal(m_sc.cpu().numpy(), scores)
     np.testing.assert_array_equal(m_pr.cpu().numpy(), probs)
+
+
+@pytest.mark.parametrize("lookup_div", ["64", "0", "100000"])
+def test_essential_posting_evaluation_is_exact(lookup_div, monkeypatch):
+    """Pruning levels >= 2 evaluate (block, query) units through their essential postings (MaxScore split per
+    1024-document block, non-essential values read from the hot / lookup value rows).  With the lookup rows
+    at their default extent, absent (BB25_LOOKUP_DIV=0) and covering every term, and with the evaluation
+    switched off, the results are the oracle's bit for bit -- queries with up to 30 terms, duplicate terms,
+    rare-only and frequent-only queries included."""
+    pkg = _pkg()
+    from bayesian_bm25_b200 import synthetic
+    from oracle import coracle
+    monkeypatch.setenv("BB25_LOOKUP_DIV", lookup_div)
+    n_docs, vocab, k = 150_000, 6000, 100
+    csc = synthetic.zipf_csc(n_docs, vocab, 45.0, seed=71, device=torch.device("cuda:0"))
+    host = _host(csc)
+    sc = pkg.BayesianBM25Scorer(alpha=2.0, beta=0.2, base_rate=0.04)
+    sc.index_from_csc(csc)
+    terms, off = synthetic.zipf_queries(240, vocab, seed=72)
+    qs = [terms[off[i]:off[i + 1]] for i in range(240)]
+    rng = np.random.default_rng(73)
+    qs += [np.asarray(x, dtype=np.int32) for x in (
+        [5999], [5998, 5997, 5996], [0, 1, 2], [0, 0, 3000, 3000], [7, 4000, 7, 4000, 7],
+        rng.integers(0, vocab, 10), rng.integers(0, vocab, 20), rng.integers(0, vocab, 30),
+        rng.integers(0, 50, 9), rng.integers(2000, vocab, 8), [], [1, 5000])]
+    flat = np.concatenate([q for q in qs]).astype(np.int32)
+    qoff = np.zeros(len(qs) + 1, dtype=np.int64)
+    qoff[1:] = np.cumsum([len(q) for q in qs])
+    params = coracle.make_params(2.0, 0.2, 0.04)
+    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, qoff, k)
+    seen = {}
+    for level, sparse in ((0, "1"), (2, "1"), (2, "0"), (3, "1"), (3, "0")):
+        monkeypatch.setenv("BB25_SPARSE", sparse)
+        sc.set_pruning(level)
+        ids, scores, probs = sc.retrieve_ids(flat, qoff, k, return_scores=True)
+        np.testing.assert_array_equal(ids, o_ids, err_msg=f"level {level} sparse {sparse}")
+        np.testing.assert_array_equal(scores.view(np.uint32), o_sc.view(np.uint32))
+        np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
+        seen[(level, sparse)] = sc.stats()
+    assert seen[(0, "1")]["units_sparse"] == 0 and seen[(2, "0")]["units_sparse"] == 0
+    assert seen[(2, "1")]["units_sparse"] > 0
