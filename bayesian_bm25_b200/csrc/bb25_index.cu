@@ -642,7 +642,11 @@ void bb25_index_destroy(bb25_index *idx) {
     cudaFree(idx->row_slot);
     for (auto &kv : idx->kth_cache) cudaFree(kv.second);
     if (idx->ws) cudaFree(idx->ws);
-    if (idx->hs_dev) cudaFree(idx->hs_dev);
+    for (int i = 0; i < 2; i++) {
+        if (idx->hs_dev[i]) cudaFree(idx->hs_dev[i]);
+        if (idx->hs_copy[i]) cudaStreamDestroy(idx->hs_copy[i]);
+        if (idx->hs_ev[i]) cudaEventDestroy(idx->hs_ev[i]);
+    }
     if (idx->hs_stream) cudaStreamDestroy(idx->hs_stream);
     if (idx->ws_ev) cudaEventDestroy(idx->ws_ev);
     if (idx->pinned) cudaFreeHost(idx->pinned);

@@ -283,8 +283,14 @@ struct bb25_index {
     int64_t fz_ne_skipped = 0, fz_sparse_units = 0, fz_sparse_docs = 0;
     double fz_traverse_ms = 0.0;
     // device + stream of the host-buffer entry points (grow-only, reused across calls)
-    void *hs_dev = nullptr;
-    size_t hs_bytes = 0;
+    // two staging slots: while one call's results travel to the host on the slot's copy stream, the next
+    // call (another thread) already computes into the other slot
+    void *hs_dev[2] = {nullptr, nullptr};
+    size_t hs_bytes[2] = {0, 0};
+    cudaStream_t hs_copy[2] = {nullptr, nullptr};
+    cudaEvent_t hs_ev[2] = {nullptr, nullptr};
+    std::mutex hs_mu[2];  // a slot serves one call at a time
+    int hs_next = 0;
     cudaStream_t hs_stream = nullptr;
     // last use of the shared workspace: calls on another stream wait for it before touching the workspace
     cudaEvent_t ws_ev = nullptr;

@@ -2515,7 +2515,7 @@ int bb25_fuse_bm25_signal(bb25_index *idx, const bb25_params *params, const int3
 static int retrieve_checked(bb25_index *idx, const bb25_params *params, const int32_t *q_terms,
                             const int64_t *q_off, int64_t n_queries, int64_t term_base, int64_t n_terms_total,
                             int k, int64_t *out_ids, float *out_scores, double *out_probs, cudaStream_t st,
-                            bool read_ends) {
+                            bool read_ends, cudaEvent_t done_ev = nullptr) {
     if (!idx) { set_error("index is NULL"); return 1; }
     if (check_params(params)) return 1;
     if (n_queries < 0 || !q_off || !out_ids || !out_probs) { set_error("bad arguments"); return 1; }
@@ -2544,6 +2544,7 @@ static int retrieve_checked(bb25_index *idx, const bb25_params *params, const in
     const int rc = retrieve_device(idx, params, q_terms, q_off, n_queries, term_base, n_terms_total, k, out_ids,
                                    out_scores, out_probs, st);
     ws_release(idx, st);
+    if (done_ev) cudaEventRecord(done_ev, st);  // still under the index lock: nothing of another call is ahead of it
     idx->st_syncs += extra_syncs;
     return rc;
 }
@@ -2574,46 +2575,61 @@ int bb25_retrieve_batch_host(bb25_index *idx, const bb25_params *params, const i
     const int64_t nt = q_off[n_queries] - q_off[0];
     if (nt < 0) { set_error("bad q_off"); return 1; }
     const size_t nk = (size_t)n_queries * (size_t)k;
-    // device staging area and stream owned by the handle, grown on demand and kept (no per-call
-    // allocation); the copies are asynchronous when the caller's buffers are page-locked
+    // Device staging slots and streams owned by the handle, grown on demand and kept (no per-call
+    // allocation); the copies are asynchronous when the caller's buffers are page-locked.  There are TWO
+    // slots: the results of this call go to the host on the slot's own copy stream after the index lock
+    // has been released, so a second thread's call computes (into the other slot) while they travel.
     const size_t o_terms = 0;
     const size_t o_off = align_up(o_terms + sizeof(int32_t) * (size_t)(nt > 0 ? nt : 1));
     const size_t o_ids = align_up(o_off + sizeof(int64_t) * (size_t)(n_queries + 1));
     const size_t o_pr = align_up(o_ids + sizeof(int64_t) * nk);
     const size_t o_sc = align_up(o_pr + sizeof(double) * nk);
     const size_t total = align_up(o_sc + sizeof(float) * nk);
+    int slot = 0;
     {
         std::lock_guard<std::mutex> lock(idx->mu);
         if (!idx->hs_stream) BB25_CUDA(cudaStreamCreateWithFlags(&idx->hs_stream, cudaStreamNonBlocking));
-        if (total > idx->hs_bytes) {
-            if (idx->hs_dev) {
-                BB25_CUDA(cudaStreamSynchronize(idx->hs_stream));
-                BB25_CUDA(cudaFree(idx->hs_dev));
-                idx->hs_dev = nullptr;
-                idx->hs_bytes = 0;
-            }
-            const size_t want = total + (total >> 3);
-            BB25_CUDA(cudaMalloc(&idx->hs_dev, want));
-            idx->hs_bytes = want;
-        }
+        slot = idx->hs_next;
+        idx->hs_next ^= 1;
     }
-    cudaStream_t st = idx->hs_stream;
-    unsigned char *base = (unsigned char *)idx->hs_dev;
+    std::lock_guard<std::mutex> slot_lock(idx->hs_mu[slot]);
+    if (!idx->hs_copy[slot]) BB25_CUDA(cudaStreamCreateWithFlags(&idx->hs_copy[slot], cudaStreamNonBlocking));
+    if (!idx->hs_ev[slot]) BB25_CUDA(cudaEventCreateWithFlags(&idx->hs_ev[slot], cudaEventDisableTiming));
+    if (total > idx->hs_bytes[slot]) {
+        if (idx->hs_dev[slot]) {
+            BB25_CUDA(cudaFree(idx->hs_dev[slot]));  // nothing of this slot is in flight: its previous call has returned
+            idx->hs_dev[slot] = nullptr;
+            idx->hs_bytes[slot] = 0;
+        }
+        const size_t want = total + (total >> 3);
+        BB25_CUDA(cudaMalloc(&idx->hs_dev[slot], want));
+        idx->hs_bytes[slot] = want;
+    }
+    cudaStream_t st = idx->hs_stream, cp = idx->hs_copy[slot];
+    unsigned char *base = (unsigned char *)idx->hs_dev[slot];
     int32_t *d_terms = (int32_t *)(base + o_terms);
     int64_t *d_off = (int64_t *)(base + o_off);
     int64_t *d_ids = (int64_t *)(base + o_ids);
     double *d_pr = (double *)(base + o_pr);
     float *d_sc = (float *)(base + o_sc);
-    if (nt > 0) BB25_CUDA(cudaMemcpyAsync(d_terms, q_terms + q_off[0], sizeof(int32_t) * (size_t)nt, cudaMemcpyHostToDevice, st));
-    BB25_CUDA(cudaMemcpyAsync(d_off, q_off, sizeof(int64_t) * (size_t)(n_queries + 1), cudaMemcpyHostToDevice, st));
-    // d_terms holds positions [q_off[0], q_off[Q]): the batch's first term is element 0 of d_terms
-    if (retrieve_checked(idx, params, d_terms - q_off[0], d_off, n_queries, q_off[0], nt, k, d_ids, d_sc, d_pr, st, false))
+    // the queries go up on the copy stream too (the compute stream may still be busy with another call)
+    if (nt > 0) BB25_CUDA(cudaMemcpyAsync(d_terms, q_terms + q_off[0], sizeof(int32_t) * (size_t)nt, cudaMemcpyHostToDevice, cp));
+    BB25_CUDA(cudaMemcpyAsync(d_off, q_off, sizeof(int64_t) * (size_t)(n_queries + 1), cudaMemcpyHostToDevice, cp));
+    BB25_CUDA(cudaStreamSynchronize(cp));
+    // d_terms holds positions [q_off[0], q_off[Q]): the batch's first term is element 0 of d_terms.  retrieve_checked
+    // takes the index lock and returns with the compute stream drained (it reads the batch report).
+    if (retrieve_checked(idx, params, d_terms - q_off[0], d_off, n_queries, q_off[0], nt, k, d_ids, d_sc, d_pr, st, false,
+                         idx->hs_ev[slot]))
         return 1;
-    BB25_CUDA(cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * nk, cudaMemcpyDeviceToHost, st));
-    if (out_scores) BB25_CUDA(cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * nk, cudaMemcpyDeviceToHost, st));
-    BB25_CUDA(cudaMemcpyAsync(out_probs, d_pr, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
-    BB25_CUDA(cudaStreamSynchronize(st));
-    idx->st_syncs++;
+    BB25_CUDA(cudaStreamWaitEvent(cp, idx->hs_ev[slot], 0));  // whatever the batch still had on the compute stream
+    BB25_CUDA(cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * nk, cudaMemcpyDeviceToHost, cp));
+    if (out_scores) BB25_CUDA(cudaMemcpyAsync(out_scores, d_sc, sizeof(float) * nk, cudaMemcpyDeviceToHost, cp));
+    BB25_CUDA(cudaMemcpyAsync(out_probs, d_pr, sizeof(double) * nk, cudaMemcpyDeviceToHost, cp));
+    BB25_CUDA(cudaStreamSynchronize(cp));
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        idx->st_syncs++;
+    }
     return 0;
 }
 

@@ -24,7 +24,7 @@ _VALID_BASE_RATE_METHODS = estimators.VALID_BASE_RATE_METHODS
 MAX_DEVICE_K = 4096      # bb25_retrieve_batch limit; larger k takes the dense path
 MAX_DENSE_K = 8192       # bb25_retrieve_one_dense limit
 QUERY_CHUNK = 16384      # queries per bb25_retrieve_batch call (bounds the workspace)
-PIPELINE_CHUNKS = 4      # retrieve(list[list[str]]): chunks whose token->id mapping overlaps the device work
+PIPELINE_CHUNKS = 3      # large batches: host calls whose copies / token->id mapping overlap the device work
 PIPELINE_MIN_CHUNK = 1024
 
 
@@ -372,13 +372,42 @@ class BayesianBM25Scorer:
         h_ids = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
         h_pr = torch.empty((nq, k), dtype=torch.float64, pin_memory=True)
         h_sc = torch.empty((nq, k), dtype=torch.float32, pin_memory=True) if return_scores else None
-        for s in range(0, nq, QUERY_CHUNK):
-            e = min(nq, s + QUERY_CHUNK)
-            self._host_call(*self._stage_host(q_terms[q_off[s]:q_off[e]], q_off[s:e + 1] - q_off[s]), k,
-                            h_ids[s:e], h_sc[s:e] if return_scores else None, h_pr[s:e])
+        bounds = self._chunk_bounds(nq)
+        if len(bounds) <= 2:
+            self._host_call(*self._stage_host(q_terms, q_off), k, h_ids, h_sc, h_pr)
+        else:
+            # two calls in flight: while one chunk's results travel to the host (the library's second
+            # staging slot and copy stream), the next chunk is already being traversed
+            with ThreadPoolExecutor(max_workers=2) as pool:
+                pending = []
+                for s, e in zip(bounds[:-1], bounds[1:]):
+                    staged = self._stage_host(q_terms[q_off[s]:q_off[e]], q_off[s:e + 1] - q_off[s])
+                    if len(pending) == 2:
+                        pending.pop(0).result()
+                    pending.append(pool.submit(self._host_call, *staged, k, h_ids[s:e],
+                                               h_sc[s:e] if return_scores else None, h_pr[s:e]))
+                for f in pending:
+                    f.result()
         if return_scores:
             return h_ids.numpy(), h_sc.numpy(), h_pr.numpy()
         return h_ids.numpy(), h_pr.numpy()
+
+    @staticmethod
+    def _chunk_bounds(nq: int, first: int = 0) -> list:
+        """Query ranges of one host call each: at most QUERY_CHUNK queries per call (bounds the workspace).
+        `first` > 0 (the string API, which maps tokens to ids chunk by chunk): a small first chunk, whose
+        mapping is the only one that cannot hide behind device work, then two or more equal chunks."""
+        if first <= 0 or nq < 2 * first:
+            n_chunks = max(1, -(-nq // QUERY_CHUNK))
+            step = -(-nq // n_chunks) if nq else 1
+            return [0] + [min(nq, (i + 1) * step) for i in range(n_chunks)]
+        rest = nq - first
+        n_chunks = max(PIPELINE_CHUNKS - 1, -(-rest // QUERY_CHUNK))
+        step = max(first, -(-rest // n_chunks))
+        bounds = [0, first]
+        while bounds[-1] < nq:
+            bounds.append(min(nq, bounds[-1] + step))
+        return bounds
 
     @staticmethod
     def _stage_host(q_terms: np.ndarray, q_off: np.ndarray):
@@ -442,21 +471,21 @@ class BayesianBM25Scorer:
         if nq < 2 * PIPELINE_MIN_CHUNK or k > MAX_DEVICE_K or k > self._num_docs:
             flat, off = self._term_ids_batch(query_tokens)
             return self.retrieve_ids(flat, off, k)
-        # Large batches: the token -> id mapping of chunk i+1 (Python dict lookups, ~2.5 us per query)
-        # runs on this thread while a worker thread sits in the C call for chunk i (ctypes drops the
-        # GIL), so the host-side mapping is hidden behind the device work.
-        step = max(PIPELINE_MIN_CHUNK, -(-nq // PIPELINE_CHUNKS))
+        # Large batches: the token -> id mapping of chunk i+1 (Python dict lookups) runs on this thread while
+        # worker threads sit in the C calls for chunks i and i-1 (ctypes drops the GIL; the library computes
+        # one while the other's results travel to the host).  Only the small first chunk's mapping is exposed.
+        bounds = self._chunk_bounds(nq, first=PIPELINE_MIN_CHUNK)
         h_ids = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
         h_pr = torch.empty((nq, k), dtype=torch.float64, pin_memory=True)
-        pending = None
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            for s in range(0, nq, step):
-                e = min(nq, s + step)
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            pending = []
+            for s, e in zip(bounds[:-1], bounds[1:]):
                 staged = self._stage_host(*self._term_ids_batch(query_tokens[s:e]))
-                if pending is not None:
-                    pending.result()
-                pending = pool.submit(self._host_call, *staged, k, h_ids[s:e], None, h_pr[s:e])
-            pending.result()
+                if len(pending) == 2:
+                    pending.pop(0).result()
+                pending.append(pool.submit(self._host_call, *staged, k, h_ids[s:e], None, h_pr[s:e]))
+            for f in pending:
+                f.result()
         return h_ids.numpy(), h_pr.numpy()
 
     def _retrieve_explained(self, query_tokens, k: int) -> "RetrievalResult":

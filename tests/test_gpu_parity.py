@@ -624,3 +624,44 @@ def test_essential_posting_evaluation_is_exact(lookup_div, monkeypatch):
         seen[(level, sparse)] = sc.stats()
     assert seen[(0, "1")]["units_sparse"] == 0 and seen[(2, "0")]["units_sparse"] == 0
     assert seen[(2, "1")]["units_sparse"] > 0
+
+
+def test_pipelined_host_calls_and_concurrent_callers():
+    """retrieve(list[list[str]]) on a large batch runs chunked host calls with two in flight (the library's two
+    staging slots: one chunk's results travel to the host while the next chunk is traversed), and two threads
+    may call retrieve_ids on one scorer at the same time.  Everything equals the single-call result and the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    pkg = _pkg()
+    from bayesian_bm25_b200 import synthetic
+    from oracle import coracle
+    n_docs, vocab, k = 60_000, 2500, 64
+    csc = synthetic.zipf_csc(n_docs, vocab, 40.0, seed=81, device=torch.device("cuda:0"))
+    host = _host(csc)
+    sc = pkg.BayesianBM25Scorer(alpha=1.8, beta=0.3, base_rate=0.05)
+    sc.index_from_csc(csc)
+    sc.set_vocabulary([f"w{i}" for i in range(vocab)])
+    flat, off = synthetic.zipf_queries(3000, vocab, seed=82)
+    params = coracle.make_params(1.8, 0.3, 0.05)
+    o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
+    ids, scs, prs = sc.retrieve_ids(flat, off, k, return_scores=True)
+    np.testing.assert_array_equal(ids, o_ids)
+    np.testing.assert_array_equal(scs.view(np.uint32), o_sc.view(np.uint32))
+    np.testing.assert_allclose(prs, o_pr, rtol=0, atol=PROB_TOL)
+    toks = [[f"w{t}" for t in flat[off[i]:off[i + 1]]] + (["not-a-word"] if i % 7 == 0 else []) for i in range(3000)]
+    s_ids, s_prs = sc.retrieve(toks, k=k)  # 3 chunks: 1024 + 2 x 988
+    np.testing.assert_array_equal(s_ids, o_ids)
+    np.testing.assert_allclose(s_prs, o_pr, rtol=0, atol=PROB_TOL)
+    halves = [(0, 1500), (1500, 3000)]
+    def call(rng_):
+        a, b = rng_
+        out = []
+        for _ in range(3):
+            out.append(sc.retrieve_ids(flat[off[a]:off[b]], off[a:b + 1] - off[a], k, return_scores=True))
+        return out
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        res = list(pool.map(call, halves))
+    for (a, b), outs in zip(halves, res):
+        for i_, s_, p_ in outs:
+            np.testing.assert_array_equal(i_, o_ids[a:b])
+            np.testing.assert_array_equal(s_.view(np.uint32), o_sc[a:b].view(np.uint32))
+            np.testing.assert_allclose(p_, o_pr[a:b], rtol=0, atol=PROB_TOL)
