@@ -474,6 +474,32 @@ def main():
         shard_timing = {k_: float(v) for k_, v in zip(sorted(shard_timing), t)}
         shard_timing["what"] = "max over ranks, one profiled (event-separated) pass"
         retr.profile = False
+    e2e_trace = None
+    if world > 1 and os.environ.get("BB25_BENCH_TRACE_E2E"):
+        # where an end-to-end sharded step spends its wall time (per rank): staging, enqueue, device, result copy
+        scorer.set_pruning(0)
+        acc_t = np.zeros(4)
+        for it in range(6):
+            barrier()
+            t = [time.perf_counter()]
+            hp = torch.empty(max(q_terms.size, 1), dtype=torch.int32, pin_memory=True)
+            hp.numpy()[:q_terms.size] = q_terms
+            ho = torch.empty(q_off.size, dtype=torch.int64, pin_memory=True)
+            ho.numpy()[:] = q_off
+            dt_, do_ = hp.to(dev, non_blocking=True), ho.to(dev, non_blocking=True)
+            t.append(time.perf_counter())
+            o_ids, _, o_pr = retr.retrieve_ids_device(dt_, do_, args.k, host_off=q_off)
+            t.append(time.perf_counter())
+            torch.cuda.synchronize()
+            t.append(time.perf_counter())
+            retr._to_host([o_ids, o_pr], "rank0")
+            t.append(time.perf_counter())
+            if it > 0:
+                acc_t += np.diff(t) * 1e3 / 5
+        gathered = [None] * world
+        dist.all_gather_object(gathered, acc_t.tolist())
+        e2e_trace = {"what": "ms per step by rank: [stage queries, enqueue (host returns), wait for the device, result to host]",
+                     "ranks": gathered}
     pr = measure(args.prune_level, sample_clocks=False)
     same = all(bool(torch.equal(x, y)) for x, y in zip(ex["out"], pr["out"]))
     out = ex["out"]
@@ -550,6 +576,7 @@ def main():
             },
             "clocks": clocks,
             "sharded_breakdown_ms_per_call": shard_timing,
+            "e2e_trace": e2e_trace,
             "e2e": {"value": args.queries * args.steps / e2e_s, "unit": "queries/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": "BayesianBM25Scorer.retrieve(list[list[str]], k): %d token strings mapped to ids on the host inside the timed region" % n_tok,
