@@ -108,6 +108,8 @@ struct FusedBlockArgs {
     int prune;
     int pair_mode;  // two fields: both in one pass (A/B accumulators) instead of one fold pass per field
     int sparse_mode;  // pair mode: essential-posting evaluation of units (pruning level >= 2)
+    uint8_t *unit_mask;  // sparse mode: per work item (block, 8-query chunk) the query slots that need the pass, written by
+                         // fused_group_kernel and read by fused_block_kernel
     unsigned long long *work_counter;
     unsigned long long *stats;  // [0] units handed out, [1] skipped by the block bound, [2] abandoned between fields,
                                 // [3] evaluated under the frequent-term restriction, [4] skipped: no essential posting,
@@ -496,7 +498,7 @@ __device__ __forceinline__ void sparse_round(const FusedBlockArgs &a, const FTer
 // field, no threshold yet); the caller runs those one by one.
 __device__ __forceinline__ unsigned group_units(const FusedBlockArgs &a, const uint4 *sfd, const uint2 *sq, int nslots, int blk,
                                                 int doc_base, int lane, unsigned &skipped, unsigned &sparse_units,
-                                                unsigned &sparse_docs) {
+                                                unsigned &sparse_docs, unsigned &hist_a, unsigned &hist_b) {
     const int qs = lane >> 3, tl = lane & 7, sh = qs * 8;
     // ladder: row entries with >= 1, 2, 3, 5, 9, 17, 33 postings; step 7: every entry (the block-max test)
     const int mycut = (tl == 0 || tl == 7) ? 1 : 1 + (1 << (tl - 1));
@@ -558,6 +560,10 @@ __device__ __forceinline__ unsigned group_units(const FusedBlockArgs &a, const u
         else if (!(bm & 0x7Fu) || n_e > kSparseMax) cls = 3;
         else cls = n_e > 0 ? 2 : 1;
         skipped += (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, cls == 1 && tl == 0));
+#ifdef BB25_NE_HIST  // tuning builds: how long are the essential lists of the units that take the pass?
+        hist_a += (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, cls == 3 && (bm & 0x7Fu) && n_e > 32 && n_e <= 64 && tl == 0));
+        hist_b += (unsigned)__popc(__ballot_sync(0xFFFFFFFFu, cls == 3 && (bm & 0x7Fu) && n_e > 64 && n_e <= 128 && tl == 0));
+#endif
         const unsigned sb3 = __ballot_sync(0xFFFFFFFFu, cls == 3 && tl == 0);
 #pragma unroll
         for (int gq = 0; gq < 4; gq++)
@@ -580,6 +586,58 @@ __device__ __forceinline__ unsigned group_units(const FusedBlockArgs &a, const u
         }
     }
     return serial;
+}
+
+// The light half of the two-field traversal at pruning level >= 2: no accumulators, few registers, twice the resident
+// warps of fused_block_kernel -- which matters because a unit here is a short chain of dependent loads (query
+// descriptors -> term records -> table entries -> essential postings -> value rows).  Per work item (block, 8-query
+// chunk) it runs group_units and leaves the query slots that need the pass in the unit mask.
+constexpr int GWARPS = 8;
+#ifndef BB25_GROUP_CTAS
+#define BB25_GROUP_CTAS 6
+#endif
+__global__ void __launch_bounds__(GWARPS * 32, BB25_GROUP_CTAS) fused_group_kernel(const __grid_constant__ FusedBlockArgs a) {
+    __shared__ __align__(16) unsigned char gsm[GWARPS * (FQC * 2 * 16 + FQC * 8)];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint4 *sfd = reinterpret_cast<uint4 *>(gsm + (size_t)warp * (FQC * 2 * 16 + FQC * 8));  // [FQC][2]: t0, m, o bits, P_tf bits
+    uint2 *sq = reinterpret_cast<uint2 *>(sfd + FQC * 2);                                   // [FQC]: q, threshold bits
+    const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
+    const int n_chunks = (n_q + FQC - 1) / FQC;
+    const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
+    unsigned int skipped = 0u, sparse_units = 0u, sparse_docs = 0u, hist_a = 0u, hist_b = 0u;
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ull);
+        item = shfl_ll(item, 0);
+        if (item >= n_items) break;
+        const int blk = a.blk_begin + (int)(item / n_chunks);
+        const int slot0 = (int)(item % n_chunks) * FQC;
+        const int nslots = min(FQC, n_q - slot0);
+        __syncwarp();
+        if (lane < nslots * 2) {
+            const int slot = lane >> 1, i = lane & 1;
+            const int my_q = a.q_list ? a.q_list[slot0 + slot] : slot0 + slot;
+            const FField &ff = a.f[i];
+            const long long t0 = ff.q_off[my_q];
+            long long m = (long long)ff.q_off[my_q + 1] - t0;
+            m = m < 0 ? 0 : (m > 32 ? 32 : m);
+            sfd[slot * 2 + i] = make_uint4((unsigned)t0, (unsigned)m, __float_as_uint(ff.q_o[my_q]), __float_as_uint(ff.q_ptf[my_q]));
+            if (i == 0) sq[slot] = make_uint2((unsigned)my_q, __float_as_uint(a.c.thr[my_q]));
+        }
+        __syncwarp();
+        const unsigned serial = group_units(a, sfd, sq, nslots, blk, blk * kBlockDocs, lane, skipped, sparse_units, sparse_docs, hist_a, hist_b);
+        if (lane == 0) a.unit_mask[item] = (uint8_t)serial;
+    }
+    if (lane == 0) {
+        if (skipped) atomicAdd(&a.stats[1], (unsigned long long)skipped);
+        if (hist_a) atomicAdd(&a.stats[4], (unsigned long long)hist_a);
+        if (hist_b) atomicAdd(&a.stats[2], (unsigned long long)hist_b);
+        if (sparse_units) atomicAdd(&a.stats[5], (unsigned long long)sparse_units);
+        if (sparse_docs) atomicAdd(&a.stats[6], (unsigned long long)sparse_docs);
+    }
 }
 
 // In FusedBlockArgs the fields are in TRAVERSAL order (cheapest index first): after each field but the last
@@ -607,15 +665,23 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
     const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
     const int n_chunks = (n_q + FQC - 1) / FQC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    // two fields at pruning level >= 2: fused_group_kernel has already skipped / evaluated most units; what is left
+    // for the pass is in the unit mask
+    const bool masked = PAIR && F == 2 && !HAS_COS && a.unit_mask != nullptr;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !masked)
         atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
-    unsigned int skipped = 0u, abandoned = 0u, restricted = 0u, ne_skipped = 0u, sparse_units = 0u, sparse_docs = 0u;
+    unsigned int skipped = 0u, abandoned = 0u, restricted = 0u;
 
     for (;;) {
         long long item = 0;
         if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ull);
         item = shfl_ll(item, 0);
         if (item >= n_items) break;
+        unsigned serial = 0xFFFFFFFFu;
+        if (masked) {
+            serial = (unsigned)a.unit_mask[item];
+            if (!serial) continue;
+        }
         const int blk = a.blk_begin + (int)(item / n_chunks);
         const int slot0 = (int)(item % n_chunks) * FQC;
         const int nslots = min(FQC, n_q - slot0);
@@ -633,12 +699,6 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
             if (i == 0) sq[slot] = make_uint2((unsigned)my_q, __float_as_uint(a.c.thr[my_q]));
         }
         __syncwarp();
-
-        // two fields at pruning level >= 2: block-max skip and essential-posting evaluation four queries at a
-        // time; the loop below runs the queries that need the pass
-        unsigned serial = 0xFFFFFFFFu;
-        if (PAIR && F == 2 && !HAS_COS && a.prune >= 2 && a.sparse_mode)
-            serial = group_units(a, sfd, sq, nslots, blk, doc_base, lane, skipped, sparse_units, sparse_docs);
 
         for (int sidx = 0; sidx < nslots; sidx++) {
             if (!((serial >> sidx) & 1u)) continue;
@@ -779,9 +839,6 @@ __global__ void __launch_bounds__(FWARPS * 32, F >= 2 ? 3 : 5) fused_block_kerne
         if (skipped) atomicAdd(&a.stats[1], (unsigned long long)skipped);
         if (abandoned) atomicAdd(&a.stats[2], (unsigned long long)abandoned);
         if (restricted) atomicAdd(&a.stats[3], (unsigned long long)restricted);
-        if (ne_skipped) atomicAdd(&a.stats[4], (unsigned long long)ne_skipped);
-        if (sparse_units) atomicAdd(&a.stats[5], (unsigned long long)sparse_units);
-        if (sparse_docs) atomicAdd(&a.stats[6], (unsigned long long)sparse_docs);
     }
 }
 
@@ -1227,6 +1284,18 @@ static int launch_fused_block_inst(const bb25_index *idx, const FusedBlockArgs &
 }
 static int launch_fused_block(const bb25_index *idx, const FusedBlockArgs &a, cudaStream_t st) {
     const bool hc = a.c.has_cos != 0;
+    if (a.unit_mask) {
+        // the light kernel first: skips / evaluates through essential postings, leaves the pass units in the mask
+        const int n_chunks = (a.n_q + FQC - 1) / FQC;
+        const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
+        if (n_items <= 0) return 0;
+        long long grid = (long long)idx->sm_count * BB25_GROUP_CTAS;
+        const long long need = (n_items + GWARPS - 1) / GWARPS;
+        if (grid > need) grid = need;
+        BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+        fused_group_kernel<<<(unsigned)grid, GWARPS * 32, 0, st>>>(a);
+        BB25_LAUNCH_CHECK();
+    }
     switch (a.c.n_fields) {
     case 1: return hc ? launch_fused_block_inst<1, true, false>(idx, a, st) : launch_fused_block_inst<1, false, false>(idx, a, st);
     case 2:
@@ -1334,6 +1403,8 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         const size_t o_bf = take(sizeof(unsigned long long) * (size_t)n_q * (size_t)kpad);
         const size_t o_bi = take(sizeof(uint32_t) * (size_t)n_q * (size_t)kpad);
         const size_t o_key = take(sizeof(unsigned long long) * (size_t)n_q * (size_t)cap);
+        const bool use_mask = n_fields == 2 && !has_cos && idx0->prune >= 2 && sparse_mode;
+        const size_t o_mask = take(use_mask ? (size_t)idx0->n_blocks * (size_t)((n_q + FQC - 1) / FQC) : 1);
         if (ensure_workspace(idx0, off)) return 1;
         unsigned char *ws = (unsigned char *)idx0->ws;
         unsigned long long *d_work = (unsigned long long *)(ws + o_ctr);
@@ -1477,6 +1548,7 @@ int bb25_retrieve_fused_batch(int n_fields, const bb25_fused_field *fields, cons
         ba.pair_mode = n_fields == 2 ? 1 : 0;
         if (const char *e = getenv("BB25_FUSED_PAIR")) ba.pair_mode = (n_fields == 2 && atoi(e) != 0) ? 1 : 0;
         ba.sparse_mode = sparse_mode;
+        ba.unit_mask = (use_mask && ba.pair_mode) ? ws + o_mask : nullptr;
         ba.work_counter = d_work;
         ba.stats = d_stats;
         float trav_ms = 0.f;

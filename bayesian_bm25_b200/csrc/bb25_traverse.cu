@@ -764,6 +764,9 @@ __global__ void __launch_bounds__(NT) select_kernel(const __grid_constant__ Sele
 #ifndef BB25_QC
 #define BB25_QC 8
 #endif
+#ifndef BB25_ENT_PREFETCH
+#define BB25_ENT_PREFETCH 0
+#endif
 constexpr int QC = BB25_QC;  // queries per warp work item
 #ifndef BB25_BK_WARPS
 #define BB25_BK_WARPS 8
@@ -1229,7 +1232,19 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
         unsigned serial = 0xFFFFFFFFu;
         if (GROUP && !EXACT && a.sparse_mode) serial = group_units<SPARSE_TAB>(a, sdesc, nslots, blk, doc_base, lane, scnt);
 
+#if BB25_ENT_PREFETCH
+        // the next query's table entries are fetched while this one is evaluated: two dependent loads
+        // (term record, block-table entry) leave the per-unit latency chain
+        TermEnt e_pf = load_term_entry<SPARSE_TAB>(a, blk, (int)sdesc[0].z + lane, lane < (int)sdesc[0].y && sdesc[0].y <= 32u);
+#endif
         for (int sidx = 0; sidx < nslots; sidx++) {
+#if BB25_ENT_PREFETCH
+            const TermEnt e_cur = e_pf;
+            if (sidx + 1 < nslots) {
+                const uint4 dn = sdesc[sidx + 1];
+                e_pf = load_term_entry<SPARSE_TAB>(a, blk, (int)dn.z + lane, lane < (int)dn.y && dn.y <= 32u);
+            }
+#endif
             if (GROUP && !((serial >> sidx) & 1u)) continue;
             const uint4 desc = sdesc[sidx];
             const int m = (int)desc.y;
@@ -1239,7 +1254,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
             const uint32_t thr_score = desc.w;
 
             if (m <= 32) {
+#if BB25_ENT_PREFETCH
+                const TermEnt e = e_cur;
+#else
                 const TermEnt e = load_term_entry<SPARSE_TAB>(a, blk, t0 + lane, lane < m);
+#endif
                 if (__ballot_sync(0xFFFFFFFFu, e.len > 0) == 0u) continue;  // no posting of any term in this block
                 if (a.prune) {
                     float ub = 0.f;
