@@ -799,6 +799,8 @@ struct BlockArgs {
     const float *lookup_vals;  // value rows of the mid-frequency terms (bb25_index::lookup_vals) or NULL
     int n_hot;                 // row slots below this are rows of dense_vals, the others rows of lookup_vals
     int sparse_mode;           // pruning level >= 2: units evaluated through their essential postings (group_units)
+    uint8_t *unit_mask;        // sparse mode: per work item (block, QC-query chunk) the query slots that need the pass,
+                               // written by group_kernel and read by block_kernel
     unsigned long long *work_counter;
     unsigned long long *stats;  // [0] (block, query) units handed out, [1] units pruned by the block-max bound, [2] units under
                                 // the level-2 restriction, [3] units evaluated through their essential postings
@@ -1201,7 +1203,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
     const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
     const int n_chunks = (n_q + QC - 1) / QC;
     const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
-    if (a.stats && blockIdx.x == 0 && threadIdx.x == 0)
+    if (a.stats && blockIdx.x == 0 && threadIdx.x == 0 && !(GROUP && !EXACT && a.unit_mask))
         atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
 
     for (;;) {
@@ -1209,6 +1211,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
         if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ull);
         item = shfl_ll(item, 0);
         if (item >= n_items) break;
+        // pruning level >= 2: group_kernel has already skipped / evaluated most units through their essential
+        // postings; the query slots left for the pass are in the unit mask
+        unsigned serial = 0xFFFFFFFFu;
+        if (GROUP && !EXACT && a.unit_mask) {
+            serial = (unsigned)a.unit_mask[item];
+            if (!serial) continue;
+        }
         const int blk = a.blk_begin + (int)(item / n_chunks);
         const int slot0 = (int)(item % n_chunks) * QC;
         const int nslots = min(QC, n_q - slot0);
@@ -1226,11 +1235,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
                                      (uint32_t)(a.thr[my_q] >> 33));
         }
         __syncwarp();
-
-        // pruning level >= 2: block-max skip and essential-posting evaluation four queries at a time; the loop
-        // below runs the queries that need the pass
-        unsigned serial = 0xFFFFFFFFu;
-        if (GROUP && !EXACT && a.sparse_mode) serial = group_units<SPARSE_TAB>(a, sdesc, nslots, blk, doc_base, lane, scnt);
 
 #if BB25_ENT_PREFETCH
         // the next query's table entries are fetched while this one is evaluated: two dependent loads
@@ -1428,7 +1432,54 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) block_kernel(const __grid_co
     if (lane == 0 && a.stats) {
         atomicAdd(&a.stats[1], (unsigned long long)scnt[0]);
         atomicAdd(&a.stats[2], (unsigned long long)scnt[1]);
-        if (GROUP && scnt[2]) atomicAdd(&a.stats[3], (unsigned long long)scnt[2]);
+    }
+}
+
+// The light half of the traversal at pruning level >= 2: no accumulators, few registers, more resident warps than
+// block_kernel -- a unit here is a short chain of dependent loads (query descriptor -> term records -> table entries ->
+// essential postings -> value rows), and warps are what hides it.  Per work item (block, QC-query chunk) it runs
+// group_units and leaves the query slots that need the pass in the unit mask.
+#ifndef BB25_GROUP_CTAS
+#define BB25_GROUP_CTAS 6
+#endif
+template <bool SPARSE_TAB>
+__global__ void __launch_bounds__(BK_WARPS * 32, BB25_GROUP_CTAS) group_kernel(const __grid_constant__ BlockArgs a) {
+    __shared__ __align__(16) uint4 gsm[BK_WARPS * (QC + 1)];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint4 *sdesc = gsm + warp * (QC + 1);
+    unsigned int *scnt = reinterpret_cast<unsigned int *>(sdesc + QC);
+    if (lane < 4) scnt[lane] = 0u;
+    __syncwarp();
+    const int n_q = a.n_q_ptr ? (int)*a.n_q_ptr : a.n_q;
+    const int n_chunks = (n_q + QC - 1) / QC;
+    const long long n_items = (long long)(a.blk_end - a.blk_begin) * n_chunks;
+    if (a.stats && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&a.stats[0], (unsigned long long)(a.blk_end - a.blk_begin) * (unsigned long long)n_q);
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(a.work_counter, 1ull);
+        item = shfl_ll(item, 0);
+        if (item >= n_items) break;
+        const int blk = a.blk_begin + (int)(item / n_chunks);
+        const int slot0 = (int)(item % n_chunks) * QC;
+        const int nslots = min(QC, n_q - slot0);
+        __syncwarp();
+        if (lane < nslots) {
+            const int my_q = a.q_list ? a.q_list[slot0 + lane] : slot0 + lane;
+            const long long t0 = a.q_off[my_q];
+            const int my_m = (int)max(0ll, (long long)a.q_off[my_q + 1] - t0);
+            sdesc[lane] = make_uint4((unsigned)my_q, (unsigned)my_m, (unsigned)(int)(t0 - a.term_base),
+                                     (uint32_t)(a.thr[my_q] >> 33));
+        }
+        __syncwarp();
+        const unsigned serial = group_units<SPARSE_TAB>(a, sdesc, nslots, blk, blk * kBlockDocs, lane, scnt);
+        if (lane == 0) a.unit_mask[item] = (uint8_t)serial;
+    }
+    __syncwarp();
+    if (lane == 0 && a.stats) {
+        if (scnt[0]) atomicAdd(&a.stats[1], (unsigned long long)scnt[0]);
+        if (scnt[2]) atomicAdd(&a.stats[3], (unsigned long long)scnt[2]);
     }
 }
 
@@ -1448,6 +1499,14 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     const long long need = (n_items + BK_WARPS - 1) / BK_WARPS;
     if (grid > need) grid = need;
     const bool sparse_tab = idx->tab_sparse_terms > 0;
+    if (!exact && pruned_cfg && a.sparse_mode && a.unit_mask) {
+        long long ggrid = (long long)idx->sm_count * BB25_GROUP_CTAS;
+        if (ggrid > need) ggrid = need;
+        if (sparse_tab) group_kernel<true><<<(unsigned)ggrid, BK_WARPS * 32, 0, st>>>(a);
+        else group_kernel<false><<<(unsigned)ggrid, BK_WARPS * 32, 0, st>>>(a);
+        BB25_LAUNCH_CHECK();
+        BB25_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+    }
 #define BB25_LAUNCH_BLOCK_G(EX, SP, CT, HF, GR)                                                                       \
     do {                                                                                                              \
         BB25_CUDA(cudaFuncSetAttribute(block_kernel<BK_WARPS, EX, SP, CT, HF, GR>,                                    \
@@ -1459,7 +1518,7 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
     if (exact) {
         if (sparse_tab) BB25_LAUNCH_BLOCK(true, true, 6, false);
         else BB25_LAUNCH_BLOCK(true, false, 6, false);
-    } else if (pruned_cfg && a.sparse_mode) {
+    } else if (pruned_cfg && a.sparse_mode && a.unit_mask) {
         if (sparse_tab) { if (half_rows) BB25_LAUNCH_BLOCK_G(false, true, BB25_BLOCK_CTAS_PRUNED, true, true); else BB25_LAUNCH_BLOCK_G(false, true, BB25_BLOCK_CTAS_PRUNED, false, true); }
         else { if (half_rows) BB25_LAUNCH_BLOCK_G(false, false, BB25_BLOCK_CTAS_PRUNED, true, true); else BB25_LAUNCH_BLOCK_G(false, false, BB25_BLOCK_CTAS_PRUNED, false, true); }
     } else if (pruned_cfg) {
@@ -2077,7 +2136,9 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     const size_t o_quant = align_up(o_badlist + sizeof(int32_t) * (size_t)n_q);
     const size_t o_info = align_up(o_quant + sizeof(unsigned long long) * 4 * (size_t)n_q);
     const size_t o_items = align_up(o_info + 2 * sizeof(longlong2) * nt);
-    const size_t o_key = align_up(o_items + sizeof(uint2) * items_cap);
+    const size_t o_mask = align_up(o_items + sizeof(uint2) * items_cap);
+    const size_t mask_bytes = sparse_mode ? (size_t)idx->n_blocks * (size_t)((n_q + QC - 1) / QC) : 1;
+    const size_t o_key = align_up(o_mask + mask_bytes);
     const size_t total = o_key + sizeof(unsigned long long) * (size_t)n_q * (size_t)cap;
     if (ensure_workspace(idx, total)) return 1;
     unsigned char *ws = (unsigned char *)idx->ws;
@@ -2190,6 +2251,7 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     ba.lookup_vals = idx->lookup_vals;
     ba.n_hot = idx->dense_vals ? idx->n_dense : 0;
     ba.sparse_mode = sparse_mode;
+    ba.unit_mask = sparse_mode ? ws + o_mask : nullptr;
     ba.work_counter = d_work;
     ba.stats = d_stats;
 
