@@ -1514,7 +1514,9 @@ static int launch_block(const bb25_index *idx, const BlockArgs &a, bool exact, c
         block_kernel<BK_WARPS, EX, SP, CT, HF, GR><<<(unsigned)grid, BK_WARPS * 32, smem, st>>>(a);                   \
     } while (0)
 #define BB25_LAUNCH_BLOCK(EX, SP, CT, HF) BB25_LAUNCH_BLOCK_G(EX, SP, CT, HF, false)
-    const bool half_rows = !exact && a.dense_h != nullptr;
+    // fp16 bound rows pay only where units are skipped or restricted (+4 % pruned); the exhaustive pass is issue-bound and
+    // the conversions cost it 0.3 % (8.8 M documents) to 4 % (shard-sized corpora): fp32 rows there (profiles/r02/half_rows_ab.txt)
+    const bool half_rows = !exact && a.dense_h != nullptr && a.prune != 0;
     if (exact) {
         if (sparse_tab) BB25_LAUNCH_BLOCK(true, true, 6, false);
         else BB25_LAUNCH_BLOCK(true, false, 6, false);
