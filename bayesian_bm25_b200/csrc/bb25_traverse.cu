@@ -375,7 +375,7 @@ struct SelectArgs {
     // select and the separate sort of the winners
     int sort_cap;
     // pre-filter of the re-scoring: a new key below prefilter * (k-th largest key as it stands) cannot be among
-    // the best k; 1 - 3e-5 for fp32 order-free sums, 1 - 6e-4 when the sums come from fp16-bound rows
+    // the best k; 1 - 3e-5 for fp32 order-free sums, 1 - 1.1e-3 when the sums come from fp16-bound rows (rounded up: <= 2^-10)
     float prefilter;
     const float *data;
     const int32_t *indices;
@@ -2297,7 +2297,10 @@ static int retrieve_device(bb25_index *idx, const bb25_params *params, const int
     // replaces the 8-pass radix select plus the sort of the winners; more keys: radix select first
     sa.sort_cap = kpad;
     // order-free sums formed from fp16-bound rows may exceed the exact score by up to 2^-11 relative per addend
-    sa.prefilter = ba.dense_h ? 0.9994f : 0.99997f;
+    // fp16 bound rows (pruned passes only, see launch_block) round every value UP by as much as one fp16 ulp = 2^-10
+    // relative, so the k-th largest key as it stands may overstate the true k-th score by that much: a key may be
+    // dropped unseen only below (1 - 1.1e-3) of it
+    sa.prefilter = (ba.dense_h && ba.prune != 0) ? 0.9989f : 0.99997f;
     const size_t sel_smem = (size_t)cap * 10 + (size_t)kpad * 9 + 260 * 4;  // keys, top, hist+st, flag, rescore list
     BB25_CUDA(cudaFuncSetAttribute(select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     // grid of a select launch whose list length is only known on the device (repair rounds)

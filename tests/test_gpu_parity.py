@@ -665,3 +665,40 @@ def test_pipelined_host_calls_and_concurrent_callers():
             np.testing.assert_array_equal(i_, o_ids[a:b])
             np.testing.assert_array_equal(s_.view(np.uint32), o_sc[a:b].view(np.uint32))
             np.testing.assert_allclose(p_, o_pr[a:b], rtol=0, atol=PROB_TOL)
+
+
+def test_fp16_bound_rows_never_hide_a_winner():
+    """The pruned passes read the frequent terms' rows as fp16 UPPER bounds (rounded up, by up to one fp16 ulp =
+    2^-10 relative).  Documents whose values are exact in fp16 then compete, in select_kernel's pre-filter, with
+    keys that overstate their documents by almost 0.1 %: 600 documents score 1.078125 (exact in fp16), the other
+    7 592 score 1.07801 but look like 1.07904 through the fp16 rows.  The true top-1000 is the 600 plus the first
+    400 of the others by id -- at every pruning level."""
+    pkg = _pkg()
+    from oracle import coracle
+    n, n_x = 8192, 600
+    va = np.full(n, 1.00001, dtype=np.float32)
+    vb = np.full(n, 0.0780, dtype=np.float32)
+    x_docs = np.arange(n - n_x, n)  # the exactly representable ones come last
+    va[x_docs], vb[x_docs] = 1.0, 0.078125
+    csc = {
+        "data": torch.from_numpy(np.concatenate([va, vb])),
+        "indices": torch.cat([torch.arange(n, dtype=torch.int32), torch.arange(n, dtype=torch.int32)]),
+        "indptr": torch.tensor([0, n, 2 * n], dtype=torch.int64),
+        "doc_len": torch.full((n,), 9, dtype=torch.int32),
+        "num_docs": n, "avgdl": 9.0,
+    }
+    sc = pkg.BayesianBM25Scorer(alpha=1.5, beta=0.3, base_rate=0.05)
+    sc.index_from_csc(csc)
+    flat = np.array([0, 1, 1, 0, 0, 1, 0], dtype=np.int32)
+    off = np.array([0, 2, 4, 7], dtype=np.int64)
+    host = _host(csc)
+    params = coracle.make_params(1.5, 0.3, 0.05)
+    for k in (1000, 700, 601):
+        o_ids, o_sc, o_pr, _ = coracle.retrieve_batch(host, params, flat, off, k)
+        assert set(x_docs.tolist()) <= set(o_ids[0].tolist())
+        for level in (0, 1, 2, 3):
+            sc.set_pruning(level)
+            ids, scores, probs = sc.retrieve_ids(flat, off, k, return_scores=True)
+            np.testing.assert_array_equal(ids, o_ids, err_msg=f"k {k} level {level}")
+            np.testing.assert_array_equal(scores.view(np.uint32), o_sc.view(np.uint32))
+            np.testing.assert_allclose(probs, o_pr, rtol=0, atol=PROB_TOL)
