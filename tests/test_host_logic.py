@@ -196,3 +196,19 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text, f"{f} mentions the oracle"
+
+
+def test_host_call_chunking():
+    """Query ranges of the pipelined host calls (scorer.py:_chunk_bounds): contiguous, complete, at most QUERY_CHUNK
+    queries per call; the string API starts with a small chunk so that only its token mapping is exposed."""
+    from bayesian_bm25_b200 import scorer as S
+    f = S.BayesianBM25Scorer._chunk_bounds
+    for nq in (0, 1, 7, 1023, 2048, 2500, 10_000, 16_384, 16_385, 40_000, 100_001):
+        for first in (0, S.PIPELINE_MIN_CHUNK):
+            b = f(nq, first)
+            assert b[0] == 0 and b[-1] == nq and all(x <= y for x, y in zip(b, b[1:]))
+            assert all(y - x <= S.QUERY_CHUNK for x, y in zip(b, b[1:]))
+            if first and nq >= 2 * first:
+                assert b[1] == first and len(b) >= 3  # a small first chunk, then the rest in chunks of at least that size
+            if not first and nq <= S.QUERY_CHUNK:
+                assert len(b) == 2  # one call
