@@ -19,6 +19,11 @@
 //    key as SURVEY 7 describes): the same bound evaluated at the per-(term, block) maxima bounds every
 //    document of the block because the conjunction is monotone in every signal; a unit below the
 //    threshold is skipped.
+//  * Essential-posting evaluation (two fields, no dense signal, pruning level >= 2; fused_group_kernel, a
+//    light kernel that runs before fused_block_kernel): MaxScore per block on the fused key -- the entries
+//    whose bound alone cannot reach the threshold are non-essential, and a unit whose other (essential)
+//    slices hold at most 32 postings is evaluated document-at-a-time, non-essential values read from the
+//    terms' value rows (hot or lookup).  The pass kernel visits only the units left in the mask.
 //  * Selection (fused_select_kernel): every candidate is evaluated EXACTLY -- per field bm25s's fp32 sum
 //    in query order, tf, the fp64 posterior; then the conjunction in signal order, the same code path
 //    (fuse_step) as the dense single-query kernels -- and the best k by (fused, doc id) are kept.  The k-th
